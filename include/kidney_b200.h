@@ -1,0 +1,171 @@
+/*
+ * libkidney_b200 -- C ABI of the B200-native (sm_100a) sampling hot path of
+ * jameshball/kidney-diffusion.
+ *
+ * The reference is pure Python (no native components, no FFI).
+ * Its boundary for this path is the Python API of imagen-pytorch==1.18.5
+ * (requirements.txt:37) as constructed in train_ultra_res_v_param.py:27-92 /
+ * train.py:28-95 / train_uncond.py:28-93 and called at
+ * sample_ultra_res.py:183-195, sample_cond.py:40-48, sample_uncond.py:49-55.
+ * Each entry point below replaces the group of PyTorch-eager library calls that
+ * imagen-pytorch issues for one step of that path; the "replaces" note on every
+ * function names the reference-side operation (module of imagen_pytorch.py as
+ * restated in oracle/imagen_oracle.py, which cites the call sites).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; every pointer is DEVICE memory
+ *    owned by the caller unless stated otherwise; the library never allocates or
+ *    frees device memory and keeps no pointer after return.
+ *  - all work is enqueued on `stream` (a cudaStream_t); no implicit device
+ *    synchronisation; every call is CUDA-graph capturable.
+ *  - return 0 on success, negative KdStatus otherwise; message via
+ *    kd_last_error() (thread-local).
+ *  - activations inside the UNet are NHWC bf16 ("[B,H,W,C]"), image state at the
+ *    sampler level is NCHW fp32 exactly as in the reference.
+ */
+#ifndef KIDNEY_B200_H_
+#define KIDNEY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* kd_stream_t; /* cudaStream_t */
+
+enum KdStatus {
+  KD_OK = 0,
+  KD_ERR_BAD_ARG = -1,
+  KD_ERR_CUDA = -2,
+  KD_ERR_LAUNCH = -3,
+  KD_ERR_ARCH = -4,
+  KD_ERR_UNSUPPORTED = -5
+};
+
+enum KdAct { KD_ACT_NONE = 0, KD_ACT_SILU = 1, KD_ACT_GELU = 2, KD_ACT_SIGMOID = 3 };
+enum KdObjective { KD_PRED_NOISE = 0, KD_PRED_V = 1, KD_PRED_X0 = 2 };
+
+int kd_version(void);
+const char* kd_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.0 (B200). No fallback exists. */
+int kd_check_device(void);
+
+/* ------------------------------------------------------------------ K1: implicit-GEMM convolution (tcgen05 + TMEM + TMA)
+ * replaces: nn.Conv2d 3x3 / 1x1 in Block.project, ResnetBlock.res_conv, Downsample (pixel-unshuffle + 1x1),
+ *           PixelShuffleUpsample (1x1 + SiLU + PixelShuffle), Parallel(3x3,1x1), and every nn.Linear applied to
+ *           image tokens (Attention/CrossAttention to_q,to_kv,to_out, ChanFeedForward).
+ * out[b,h,w,n] = act( sum_{tap,c} A[b, h+dy(tap), w+dx(tap), c] * Wt[n, tap, c] + bias[n] )
+ *                + addend_scale[b,n] * addend[b,h,w,n]
+ * A is the channel concatenation of two NHWC bf16 sources (xa: Ca channels, xb: Cb channels; Cb may be 0).
+ */
+typedef struct KdConvDesc {
+  int mode;         /* 0: ksize x ksize, stride 1, zero pad ksize/2.  1: 2x2 stride-2 "pixel-unshuffle" taps (Downsample);
+                       2: plain GEMM on a [M,K] row-major matrix given as xa (H=1, W=M, Ca=K) */
+  int B, H, W;      /* OUTPUT batch / height / width (mode 1: the input is [B,2H,2W,C]) */
+  int Ca, Cb;       /* input channels of the two sources; each a multiple of 64 */
+  int Cout;         /* output channels (multiple of 8) */
+  int ksize;        /* 1 or 3 for mode 0; ignored otherwise */
+  int act;          /* KdAct applied before the addend */
+  int out_mode;     /* 0: NHWC [B,H,W,Cout].  1: pixel-shuffle(2): weight rows ordered (dy,dx,c) -> out [B,2H,2W,Cout/4] */
+  int out_f32;      /* 0: bf16 output, 1: fp32 output */
+  int addend_f32;   /* dtype of addend (same layout as out) */
+} KdConvDesc;
+
+int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
+                 const void* w /* bf16 [Cout, taps*(Ca+Cb)], K ordered (tap, channel) */, const float* bias /* [Cout] or NULL */,
+                 const void* addend /* or NULL */, const float* addend_scale /* [B,Cout] or NULL (=1) */, void* out,
+                 kd_stream_t stream);
+
+/* ------------------------------------------------------------------ small-M linear (time / conditioning towers, GCA MLP)
+ * replaces: nn.Linear on (B, features) tensors: to_time_hiddens, to_time_cond, to_time_tokens, ResnetBlock.time_mlp,
+ *           GlobalContext.net, CrossAttention.to_kv on the conditioning tokens.
+ * y[m, n] = post_act( sum_k pre_act(x[m,k]) * w[n,k] + bias[n] ), fp32 everywhere, M <= 4096 rows. */
+int kd_linear_small(const float* x, int M, int K, long ldx, const float* w, const float* bias, float* y, int N, long ldy,
+                    int pre_act, int post_act, kd_stream_t stream);
+
+/* replaces: LearnedSinusoidalPosEmb.forward -> out[b] = [t, sin(2 pi t w), cos(2 pi t w)] (1 + 2*half values) */
+int kd_sinu_emb(const float* t, const float* weights, int B, int half, float* out, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ K3: GroupNorm (statistics / finalize / apply)
+ * replaces: nn.GroupNorm + (scale+1)*x+shift + SiLU in Block.forward, including GroupNorm over the channel concat
+ *           cat(x, skip * 2^-0.5) of the up path (two sources, the second pre-scaled by src_scale).
+ * kd_gn_stats writes deterministic per-block partial sums  partial[b][blk][g] = {sum, sumsq} over the channels of this
+ * source that fall into global group g (global channel = c_offset + c; group = global channel / group_size). */
+int kd_gn_stats(const void* x /* bf16 [B,HW,C] */, int B, long HW, int C, int c_offset, int group_size, int num_groups,
+                float* partial /* [B][nblk][num_groups][2] */, int nblk, kd_stream_t stream);
+int kd_gn_finalize(const float* partial_a, int nblk_a, float scale_a, const float* partial_b, int nblk_b, float scale_b, int B,
+                   int num_groups, double count /* elements per (b, group) */, float eps, float* mean_rstd /* [B][G][2] */,
+                   kd_stream_t stream);
+/* y = act( ((x*src_scale - mean) * rstd * gamma + beta) * (scale + 1) + shift ), bf16 out.
+ * scale_shift: [B][2*Ctot] fp32 laid out as time_mlp output (scale = first Ctot, shift = last Ctot) or NULL. */
+int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int group_size, int num_groups, float src_scale,
+                const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift, int Ctot, int act,
+                kd_stream_t stream);
+
+/* ------------------------------------------------------------------ K4: GlobalContext gate
+ * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */
+int kd_rowdot(const void* x /* bf16 [B,HW,C] */, const float* w /* [C] */, const float* bias /* [1] or NULL */, float* out /* [B,HW] */,
+              int B, long HW, int C, kd_stream_t stream);
+int kd_gca_pool(const void* x, const float* logits, int B, long HW, int C, int nblk, float* part /* [B][nblk][C] */,
+                float* ml /* [B][nblk][2] = {max, sumexp} */, kd_stream_t stream);
+int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled /* [B][C] */, kd_stream_t stream);
+/* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); bf16 in/out */
+int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, int B, long HW, int C, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ LayerNorm over channels of NHWC tokens
+ * replaces: imagen-pytorch LayerNorm / ChanLayerNorm (gain only, eps 1e-5) and nn.LayerNorm (gain + bias).
+ * y = (x - mean) * rsqrt(var + eps) * g (+ bias) (+ residual) */
+int kd_layernorm_bf16(const void* x, const float* g, const float* bias, const void* residual, void* y, long M, int C, float eps,
+                      kd_stream_t stream);
+int kd_layernorm_f32(const float* x, const float* g, const float* bias, float* y, long M, int C, float eps, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ K5: attention
+ * replaces: Attention.forward (multi-query: one shared 64-d K/V head, null k/v and optional context k/v prepended) and
+ *           CrossAttention.forward (full multi-head K/V from <= 64 conditioning tokens + null k/v). */
+int kd_kv_assemble(const void* qkv /* bf16 [B,N,ld] */, long ld, int kv_col, const float* ctx_kv /* [B,Jc,128] or NULL */, int Jc,
+                   const float* null_kv /* [2,64] */, void* kv_out /* bf16 [B, Jc+1+N, 128] */, int B, int N, kd_stream_t stream);
+int kd_attn_mqa(const void* q /* bf16 [B,N,*] */, long ldq, const void* kv /* bf16 [B,J,128] */, void* out /* bf16 [B,N,heads*64] */,
+                int B, int N, int J, int heads, float scale, kd_stream_t stream);
+int kd_attn_cross(const void* q, long ldq, const float* kv /* [B,Jc,2*heads*64] */, const float* null_kv /* [2,64] */,
+                  void* out /* bf16 [B,N,heads*64] */, int B, int N, int Jc, int heads, float scale, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ init / final convolutions
+ * replaces: CrossEmbedLayer (3 convs k=3,7,15 concatenated) via an im2col panel consumed by kd_conv_gemm mode 2,
+ *           and Unet.final_conv (3x3, Cout = 3) on cat(x, lowres_cond_img). */
+int kd_im2col_nchw(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int W, int ksize, void* out /* bf16 [B*H*W, Kp] */,
+                   int Kp, kd_stream_t stream);
+int kd_final_conv(const void* xa /* bf16 [B,H,W,Ca] */, int Ca, const float* xb /* fp32 NCHW [B,Cb,H,W] or NULL */, int Cb,
+                  const float* w /* fp32 [Cout][3][3][Ca+Cb] */, const float* bias, float* out /* fp32 NCHW [B,Cout,H,W] */, int B,
+                  int H, int W, int Cout, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ K6 / K7: sampler update
+ * replaces: Imagen.p_mean_variance + p_sample (x0 from eps / v, dynamic threshold = torch.quantile(|x0|, 0.95) per sample,
+ *           clamp(min=1), q_posterior mean, ancestral noise), the RePaint blend / re-noise of p_sample_loop and the
+ *           final clamp + paste + un-normalise.  All NCHW fp32, scalars computed by the caller in fp32. */
+size_t kd_dynthresh_workspace_bytes(int B);
+int kd_dynthresh(const float* x_t, const float* pred, int B, long n_per, int objective, float alpha, float sigma, long rank_lo,
+                 long rank_hi, float weight, void* workspace, size_t ws_bytes, float* s_out /* [B] */, kd_stream_t stream);
+int kd_ddpm_step(const float* x_t, const float* pred, const float* noise, const float* s /* [B] or NULL: static clamp */,
+                 float* out, float* x0_out /* or NULL */, int B, long n_per, int objective, float alpha, float sigma,
+                 float one_minus_c, float c, float alpha_next, float std, const float* renoise /* or NULL */, float rn_k1,
+                 float rn_num, float rn_alpha, kd_stream_t stream);
+int kd_inpaint_blend(float* img, const float* inpaint, const uint8_t* mask /* [B,HW] */, const float* noise /* or NULL */,
+                     float alpha, float sigma, int B, int C, long HW, kd_stream_t stream);
+int kd_finalize_image(float* img, const float* inpaint /* or NULL */, const uint8_t* mask, int B, int C, long HW,
+                      kd_stream_t stream);
+int kd_q_sample(const float* x0, const float* noise, float alpha, float sigma, float* out, long n, kd_stream_t stream);
+/* counter-based N(0,1): Philox4x32-10 keyed by (seed, key), Box-Muller */
+int kd_randn(float* out, long n, uint64_t seed, uint64_t key, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ K8: overlap-border pack for the patch-grid sampler
+ * replaces: the inpaint canvas construction of generate_image_distributed (sample_ultra_res.py:149-170): copies the
+ *           overlap strips of up to three finished neighbour patches into inpaint_patch / inpaint_mask. */
+int kd_border_pack(float* inpaint /* [3,S,S] */, uint8_t* mask /* [S,S] */, const float* above, const float* side,
+                   const float* corner /* each [3,S,S] or NULL */, int S, int overlap_pos, int orientation, kd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,104 @@
+// Shared host/device helpers for libkidney_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/kidney_b200.h"
+
+// ---------------------------------------------------------------- host-side error plumbing
+void kd_set_error(const char* fmt, ...);
+
+#define KD_FAIL(code, ...)            \
+  do {                                \
+    kd_set_error(__VA_ARGS__);        \
+    return (code);                    \
+  } while (0)
+
+#define KD_REQUIRE(cond, ...)                          \
+  do {                                                 \
+    if (!(cond)) KD_FAIL(KD_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define KD_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      KD_FAIL(KD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define KD_LAUNCH_CHECK()                                                                \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      KD_FAIL(KD_ERR_LAUNCH, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int kd_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+int kd_num_sms();
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+struct __align__(16) bf16x8 {
+  bf162 v[4];
+};
+
+__device__ __forceinline__ void bf16x8_to_float(const bf16x8& in, float* out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(in.v[i]);
+    out[2 * i] = f.x;
+    out[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ bf16x8 float_to_bf16x8(const float* in) {
+  bf16x8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+  return o;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  bf162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == KD_ACT_SILU) return silu_f(x);
+  if (act == KD_ACT_GELU) return gelu_f(x);
+  if (act == KD_ACT_SIGMOID) return sigmoid_f(x);
+  return x;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit global access (read-once / write-once data)
+__device__ __forceinline__ int4 ld_stream(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+#endif

@@ -1,0 +1,464 @@
+// K1: implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA).
+//
+//   M = B*H*W output pixels (tile = TB x TH x TW = 128 pixels), N = Cout, K = taps * (Ca + Cb).
+//   A operand: for k-block (tap, 64-channel chunk) one TMA tiled load of a [TB,TH,TW,64] box of the NHWC bf16
+//              activation tensor, shifted by the tap offset; out-of-bounds coordinates are zero-filled by the TMA unit,
+//              which implements the convolution's zero padding.  The box lands in shared memory as 128 rows x 128 B with
+//              the 128-byte swizzle, i.e. exactly the canonical K-major SWIZZLE_128B UMMA operand layout.
+//   B operand: [BN, 64] box of the packed weight matrix [Cout, K] (K-major), same swizzle.
+//   D        : 128 x BN fp32 accumulator in tensor memory; read back by 4 epilogue warps with tcgen05.ld.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).  Two CTAs are resident per SM (3-stage ring,
+// <= 100 KB smem each, 128 TMEM columns each) so one CTA's epilogue overlaps the other CTA's main loop.
+#include <cuda.h>
+#include <mutex>
+
+#include "kd_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+
+struct ConvParams {
+  int mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, out_f32, addend_f32;
+  int TW, TH, TB;
+  int tiles_w, tiles_h, tiles_b, n_tiles;
+  int chunks_a, chunks_per_tap, num_kb;
+  const float* bias;
+  const void* addend;
+  const float* addend_scale;
+  void* out;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 "version 1"):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  // instruction descriptor: D = fp32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // control block after the operand ring
+  uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* bias_smem = reinterpret_cast<float*>(ctrl + 128);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int n_tile = blockIdx.x % p.n_tiles;
+  int m_tile = blockIdx.x / p.n_tiles;
+  const int tile_w = m_tile % p.tiles_w;
+  m_tile /= p.tiles_w;
+  const int tile_h = m_tile % p.tiles_h;
+  const int tile_b = m_tile / p.tiles_h;
+  const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, b0 = tile_b * p.TB;
+  const int n0 = n_tile * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    if (p.Cb > 0) tma_prefetch_desc(&map_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  if (warp >= 2) {
+    for (int j = threadIdx.x - 64; j < BN; j += 128) {
+      const int n = n0 + j;
+      bias_smem[j] = (p.bias != nullptr && n < p.Cout) ? p.bias[n] : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (one elected lane)
+    if (lane == 0) {
+      const int pad = (p.mode == 0) ? (p.ksize >> 1) : 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const int tap = kb / p.chunks_per_tap;
+        const int ch = kb - tap * p.chunks_per_tap;
+        const bool src_b = ch >= p.chunks_a;
+        const CUtensorMap* map = src_b ? &map_b : &map_a;
+        const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
+        const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+        if (p.mode == 1) {
+          // input viewed as [B, H, 2(dy), W, 2C]: tap = dy*2 + dx selects the dx half of the 2C axis
+          const int dy = tap >> 1, dx = tap & 1;
+          const int C = src_b ? p.Cb : p.Ca;
+          tma_load_5d(a_dst, map, fb, dx * C + c0, w0, dy, h0, b0);
+        } else {
+          const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+          tma_load_5d(a_dst, map, fb, c0, w0 + kx - pad, h0 + ky - pad, b0, 0);
+        }
+        tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, fb, kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one elected lane)
+    if (lane == 0) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+        const uint64_t a_desc = make_sw128_desc(a_addr);
+        const uint64_t b_desc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(smem_u32(tmem_full_bar));  // accumulator complete
+    }
+  } else {
+    // ================================================================ epilogue: TMEM -> registers -> global
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
+    const int tw = r % p.TW;
+    const int th = (r / p.TW) % p.TH;
+    const int tb = r / (p.TW * p.TH);
+    const int b = b0 + tb, h = h0 + th, w = w0 + tw;
+    const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
+
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+
+    const int Cq = p.Cout >> 2;  // channels per pixel-shuffle quadrant
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
+      tmem_ld_wait();
+      const int nc = n0 + chunk * 32;
+      if (!row_ok || nc >= p.Cout) continue;
+
+      long long out_off;   // element offset of column nc for this row
+      long long add_off;
+      if (p.out_mode == 1) {
+        const int q4 = nc / Cq, c = nc - q4 * Cq;
+        const int dy = q4 >> 1, dx = q4 & 1;
+        out_off = (((long long)b * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * Cq + c;
+      } else {
+        out_off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc;
+      }
+      add_off = out_off;
+      const float* gate = p.addend_scale ? p.addend_scale + (long long)b * p.Cout + nc : nullptr;
+
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns
+        if (nc + g * 8 + 8 > p.Cout) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = __uint_as_float(acc[g * 8 + j]) + bias_smem[chunk * 32 + g * 8 + j];
+          v[j] = apply_act(v[j], p.act);
+        }
+        if (p.addend != nullptr) {
+          float a[8];
+          if (p.addend_f32) {
+            const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + add_off + g * 8);
+            float4 a0 = ap[0], a1 = ap[1];
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+          } else {
+            bf16x8 raw = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.addend) + add_off + g * 8);
+            bf16x8_to_float(raw, a);
+          }
+          if (gate != nullptr) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(gate + g * 8 + 4);
+            a[0] *= g0.x; a[1] *= g0.y; a[2] *= g0.z; a[3] *= g0.w; a[4] *= g1.x; a[5] *= g1.y; a[6] *= g1.z; a[7] *= g1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += a[j];
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + g * 8);
+          op[0] = make_float4(v[0], v[1], v[2], v[3]);
+          op[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.out) + out_off + g * 8) = float_to_bf16x8(v);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) KD_FAIL(KD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdims[5], gstr[4];
+  cuuint32_t gbox[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) KD_FAIL(KD_ERR_BAD_ARG, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (gstr[i] % 16 != 0) KD_FAIL(KD_ERR_BAD_ARG, "TMA stride %d = %llu not a multiple of 16 bytes", i, (unsigned long long)gstr[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) KD_FAIL(KD_ERR_BAD_ARG, "TMA base pointer not 16-byte aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) KD_FAIL(KD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return KD_OK;
+}
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// activation tensor map for one source with C channels
+int make_act_map(CUtensorMap* m, const KdConvDesc* d, const void* x, int C, int TW, int TH, int TB) {
+  if (d->mode == 1) {
+    const uint64_t Hi = 2ull * d->H, Wi = 2ull * d->W;
+    const uint64_t dims[5] = {2ull * C, (uint64_t)d->W, 2ull, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t str[4] = {2ull * C * 2, Wi * C * 2, 2 * Wi * C * 2, Hi * Wi * C * 2};
+    const uint32_t box[5] = {(uint32_t)BK, (uint32_t)TW, 1u, (uint32_t)TH, (uint32_t)TB};
+    return encode_map(m, x, 5, dims, str, box);
+  }
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B, 1ull};
+  const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2,
+                           (uint64_t)d->B * d->H * d->W * C * 2};
+  const uint32_t box[5] = {(uint32_t)BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB, 1u};
+  return encode_map(m, x, 5, dims, str, box);
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, long long grid,
+           cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 /*align slack*/ + 128 /*barriers*/ + BN * 4 /*bias*/;
+  static bool configured = false;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured) {
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured = true;
+    }
+  }
+  conv_gemm_kernel<BN, STAGES><<<(unsigned)grid, NUM_THREADS, SMEM, stream>>>(ma, mb, mw, p);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+}  // namespace
+
+extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
+                            const void* addend, const float* addend_scale, void* out, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(d && xa && w && out, "kd_conv_gemm: null argument");
+  KD_REQUIRE(d->mode >= 0 && d->mode <= 2, "kd_conv_gemm: bad mode %d", d->mode);
+  KD_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "kd_conv_gemm: bad output shape %dx%dx%d", d->B, d->H, d->W);
+  KD_REQUIRE(d->Ca > 0 && d->Ca % BK == 0 && d->Cb >= 0 && d->Cb % BK == 0,
+             "kd_conv_gemm: channel counts must be multiples of %d (Ca=%d Cb=%d)", BK, d->Ca, d->Cb);
+  KD_REQUIRE(d->Cb == 0 || xb != nullptr, "kd_conv_gemm: Cb > 0 but xb is null");
+  KD_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, "kd_conv_gemm: Cout=%d must be a multiple of 8", d->Cout);
+  KD_REQUIRE(d->mode != 0 || d->ksize == 1 || d->ksize == 3, "kd_conv_gemm: ksize must be 1 or 3");
+  KD_REQUIRE(d->out_mode == 0 || (d->out_mode == 1 && d->Cout % 128 == 0),
+             "kd_conv_gemm: pixel-shuffle output needs Cout %% 128 == 0 (got %d)", d->Cout);
+  KD_REQUIRE(d->mode != 2 || (d->H == 1 && d->B == 1 && d->Cb == 0), "kd_conv_gemm: mode 2 expects B=H=1, single source");
+
+  const int taps = (d->mode == 1) ? 4 : (d->mode == 0 ? d->ksize * d->ksize : 1);
+  ConvParams p;
+  p.mode = d->mode == 2 ? 0 : d->mode;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.Ca = d->Ca; p.Cb = d->Cb; p.Cout = d->Cout;
+  p.ksize = (d->mode == 0) ? d->ksize : 1;
+  p.act = d->act; p.out_mode = d->out_mode; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
+  p.TH = pow2_ceil(d->H) < 8 ? pow2_ceil(d->H) : 8;
+  {
+    const int wmax = BM / p.TH;
+    p.TW = pow2_ceil(d->W) < wmax ? pow2_ceil(d->W) : wmax;
+  }
+  p.TB = BM / (p.TH * p.TW);
+  p.tiles_w = kd_ceil_div(d->W, p.TW);
+  p.tiles_h = kd_ceil_div(d->H, p.TH);
+  p.tiles_b = kd_ceil_div(d->B, p.TB);
+  p.chunks_a = d->Ca / BK;
+  p.chunks_per_tap = (d->Ca + d->Cb) / BK;
+  p.num_kb = taps * p.chunks_per_tap;
+  p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out;
+
+  const int BN = d->Cout >= 128 ? 128 : 64;
+  p.n_tiles = kd_ceil_div(d->Cout, BN);
+  const long long grid = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  KD_REQUIRE(grid > 0 && grid < 2147483647LL, "kd_conv_gemm: grid too large");
+
+  KdConvDesc dd = *d;
+  if (d->mode == 2) dd.mode = 0;
+  CUtensorMap ma, mb, mw;
+  int rc = make_act_map(&ma, &dd, xa, d->Ca, p.TW, p.TH, p.TB);
+  if (rc) return rc;
+  if (d->Cb > 0) {
+    rc = make_act_map(&mb, &dd, xb, d->Cb, p.TW, p.TH, p.TB);
+    if (rc) return rc;
+  } else {
+    mb = ma;
+  }
+  {
+    const uint64_t Ktot = (uint64_t)taps * (d->Ca + d->Cb);
+    const uint64_t dims[2] = {Ktot, (uint64_t)d->Cout};
+    const uint64_t str[1] = {Ktot * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    rc = encode_map(&mw, w, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  if (BN == 128) return launch<128, 3>(ma, mb, mw, p, grid, stream);
+  return launch<64, 4>(ma, mb, mw, p, grid, stream);
+}

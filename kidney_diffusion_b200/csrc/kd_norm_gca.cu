@@ -1,0 +1,456 @@
+// HBM-bound NHWC bf16 kernels around the convolutions: GroupNorm (stats / finalize / apply), GlobalContext pooling,
+// gate * h + residual, LayerNorm over channels.  All reductions are fixed-order (no float atomics) so results are
+// identical run to run and across GPU counts.
+//
+// Common thread mapping for [B, HW, C] tensors: a pixel's C channels are split into C/8 "octets" (one 16-byte load);
+// a block of T = (256 / oct) * oct threads covers T / oct pixels at a time, every thread keeps the same octet for its
+// whole pixel loop, so per-channel constants (gamma, beta, scale/shift, gate) are loaded once per thread.
+#include "kd_common.cuh"
+
+namespace {
+
+__host__ __device__ inline int threads_for_oct(int oct) { return oct >= 256 ? 256 : (256 / oct) * oct; }
+
+// ------------------------------------------------------------------------------------------------ GroupNorm stats
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long HW, int C, int c_offset, int group_size, int G,
+                                float* __restrict__ partial, int nblk) {
+  extern __shared__ float sm[];  // [T][2]
+  const int oct = C >> 3;
+  const int T = blockDim.x;
+  const int lanes = T / oct;  // pixels processed in parallel
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int b = blockIdx.y;
+  const long per = (HW + nblk - 1) / nblk;
+  const long p0 = (long)blockIdx.x * per;
+  const long p1 = p0 + per < HW ? p0 + per : HW;
+  const bf16* xb = x + (long)b * HW * C + (long)o * 8;
+  float s = 0.f, ss = 0.f;
+  for (long p = p0 + pl; p < p1; p += lanes) {
+    int4 raw = ld_stream(xb + p * C);
+    float v[8];
+    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s += v[j];
+      ss += v[j] * v[j];
+    }
+  }
+  sm[threadIdx.x * 2] = s;
+  sm[threadIdx.x * 2 + 1] = ss;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float gs = 0.f, gss = 0.f;
+    // octets of this source whose global channel falls into group g, all pixel lanes, fixed order
+    for (int oo = 0; oo < oct; ++oo) {
+      if ((c_offset + oo * 8) / group_size != g) continue;
+      for (int l = 0; l < lanes; ++l) {
+        gs += sm[(l * oct + oo) * 2];
+        gss += sm[(l * oct + oo) * 2 + 1];
+      }
+    }
+    float* out = partial + (((long)b * nblk + blockIdx.x) * G + g) * 2;
+    out[0] = gs;
+    out[1] = gss;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ pa, int nblk_a, float scale_a, const float* __restrict__ pb,
+                                   int nblk_b, float scale_b, int G, double count, float eps, float* __restrict__ mean_rstd) {
+  const int b = blockIdx.x;
+  const int g = threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < nblk_a; ++k) {
+    const float* q = pa + (((long)b * nblk_a + k) * G + g) * 2;
+    s += (double)q[0] * scale_a;
+    ss += (double)q[1] * scale_a * scale_a;
+  }
+  if (pb != nullptr) {
+    for (int k = 0; k < nblk_b; ++k) {
+      const float* q = pb + (((long)b * nblk_b + k) * G + g) * 2;
+      s += (double)q[0] * scale_b;
+      ss += (double)q[1] * scale_b * scale_b;
+    }
+  }
+  const double mean = s / count;
+  double var = ss / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[((long)b * G + g) * 2] = (float)mean;
+  mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long HW, int C, int c_offset, int group_size,
+                                int G, float src_scale, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ scale_shift, int Ctot, int act,
+                                int nblk) {
+  const int oct = C >> 3;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int b = blockIdx.y;
+  const int cg = c_offset + o * 8;  // global channel of this thread's first element
+  const int g = cg / group_size;
+  const float mean = mean_rstd[((long)b * G + g) * 2];
+  const float rstd = mean_rstd[((long)b * G + g) * 2 + 1];
+  float A[8], Bc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ga = gamma[cg + j], be = beta[cg + j];
+    float a = rstd * ga, c = be - mean * rstd * ga;
+    if (scale_shift != nullptr) {
+      const float sc = scale_shift[(long)b * 2 * Ctot + cg + j] + 1.0f;
+      const float sh = scale_shift[(long)b * 2 * Ctot + Ctot + cg + j];
+      a *= sc;
+      c = c * sc + sh;
+    }
+    A[j] = a * src_scale;
+    Bc[j] = c;
+  }
+  const long per = (HW + nblk - 1) / nblk;
+  const long p0 = (long)blockIdx.x * per;
+  const long p1 = p0 + per < HW ? p0 + per : HW;
+  const bf16* xb = x + (long)b * HW * C + (long)o * 8;
+  bf16* yb = y + (long)b * HW * C + (long)o * 8;
+  for (long p = p0 + pl; p < p1; p += lanes) {
+    int4 raw = ld_stream(xb + p * C);
+    float v[8];
+    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(A[j], v[j], Bc[j]), act);
+    bf16x8 o8 = float_to_bf16x8(v);
+    *reinterpret_cast<int4*>(yb + p * C) = *reinterpret_cast<int4*>(&o8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GlobalContext
+// logits[b, n] = sum_c x[b,n,c] * w[c] + bias : one warp per pixel (two pixels per warp when C = 128).
+__global__ void rowdot_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                              float* __restrict__ out, long rows, int C) {
+  const int oct = C >> 3;
+  const int sub = oct < 32 ? oct : 32;  // lanes cooperating on one pixel (power of two)
+  const int ppw = 32 / sub;             // pixels per warp
+  const int lane = threadIdx.x & 31;
+  const long warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const int sl = lane % sub, sp = lane / sub;
+  const float bb = bias ? bias[0] : 0.f;
+  for (long r0 = warp_global * ppw; r0 < rows; r0 += nwarps * ppw) {
+    const long r = r0 + sp;
+    float acc = 0.f;
+    if (r < rows) {
+      for (int o = sl; o < oct; o += sub) {
+        int4 raw = ld_stream(x + r * C + o * 8);
+        float v[8];
+        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+        const float4 w0 = *reinterpret_cast<const float4*>(w + o * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + o * 8 + 4);
+        acc += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+      }
+    }
+    for (int off = sub >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (sl == 0 && r < rows) out[r] = acc + bb;
+  }
+}
+
+// Softmax-weighted channel pooling, one block per (pixel chunk, b): partial[b][blk][c] = sum_n exp(l_n - m_blk) x[n,c]
+__global__ void gca_pool_kernel(const bf16* __restrict__ x, const float* __restrict__ logits, long HW, int C, int nblk,
+                                float* __restrict__ part, float* __restrict__ ml) {
+  extern __shared__ float sm[];  // max(T, lanes*C) floats
+  __shared__ float s_red[32];
+  __shared__ float s_m;
+  const int oct = C >> 3;
+  const int T = blockDim.x;
+  const int lanes = T / oct;
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int b = blockIdx.y;
+  const long per = (HW + nblk - 1) / nblk;
+  const long p0 = (long)blockIdx.x * per;
+  const long p1 = p0 + per < HW ? p0 + per : HW;
+  const float* lg = logits + (long)b * HW;
+  // block max of the chunk's logits
+  float m = -INFINITY;
+  for (long p = p0 + threadIdx.x; p < p1; p += T) m = fmaxf(m, lg[p]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = -INFINITY;
+    for (int i = 0; i < (T + 31) / 32; ++i) mm = fmaxf(mm, s_red[i]);
+    s_m = mm;
+  }
+  __syncthreads();
+  m = s_m;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float l = 0.f;
+  const bf16* xb = x + (long)b * HW * C + (long)o * 8;
+  for (long p = p0 + pl; p < p1; p += lanes) {
+    const float e = __expf(lg[p] - m);
+    int4 raw = ld_stream(xb + p * C);
+    float v[8];
+    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(e, v[j], acc[j]);
+    l += e;
+  }
+  // reduce over pixel lanes in fixed order
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[(pl * oct + o) * 8 + j] = acc[j];
+  __syncthreads();
+  float* outp = part + ((long)b * nblk + blockIdx.x) * C;
+  for (int c = threadIdx.x; c < C; c += T) {
+    float s = 0.f;
+    for (int q = 0; q < lanes; ++q) s += sm[(q * oct + (c >> 3)) * 8 + (c & 7)];
+    outp[c] = s;
+  }
+  __syncthreads();
+  // sum of exp: only octet-0 threads hold distinct pixels
+  sm[threadIdx.x] = (o == 0) ? l : 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < T; ++i) s += sm[i];
+    ml[((long)b * nblk + blockIdx.x) * 2] = m;
+    ml[((long)b * nblk + blockIdx.x) * 2 + 1] = s;
+  }
+}
+
+__global__ void gca_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ml, int nblk, int C,
+                                    float* __restrict__ pooled) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  float M = -INFINITY;
+  for (int k = 0; k < nblk; ++k) M = fmaxf(M, ml[((long)b * nblk + k) * 2]);
+  float L = 0.f, s = 0.f;
+  for (int k = 0; k < nblk; ++k) {
+    const float mk = ml[((long)b * nblk + k) * 2];
+    const float f = (mk == -INFINITY) ? 0.f : __expf(mk - M);
+    L += f * ml[((long)b * nblk + k) * 2 + 1];
+    if (c < C) s += f * part[((long)b * nblk + k) * C + c];
+  }
+  if (c < C) pooled[(long)b * C + c] = s / L;
+}
+
+__global__ void gate_residual_kernel(const bf16* __restrict__ h, const float* __restrict__ gate, const bf16* __restrict__ res,
+                                     bf16* __restrict__ out, long HW, int C, int nblk) {
+  const int oct = C >> 3;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int b = blockIdx.y;
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = gate ? gate[(long)b * C + o * 8 + j] : 1.0f;
+  const long per = (HW + nblk - 1) / nblk;
+  const long p0 = (long)blockIdx.x * per;
+  const long p1 = p0 + per < HW ? p0 + per : HW;
+  const long base = (long)b * HW * C + (long)o * 8;
+  for (long p = p0 + pl; p < p1; p += lanes) {
+    int4 raw = ld_stream(h + base + p * C);
+    float v[8];
+    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+    if (res != nullptr) {
+      int4 rr = ld_stream(res + base + p * C);
+      float r[8];
+      bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rr), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], g[j], r[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= g[j];
+    }
+    bf16x8 o8 = float_to_bf16x8(v);
+    *reinterpret_cast<int4*>(out + base + p * C) = *reinterpret_cast<int4*>(&o8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm (one warp per token)
+template <bool F32>
+__global__ void layernorm_kernel(const void* __restrict__ x_, const float* __restrict__ g, const float* __restrict__ bias,
+                                 const void* __restrict__ res_, void* __restrict__ y_, long M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  float s = 0.f, ss = 0.f;
+  if (F32) {
+    const float* x = reinterpret_cast<const float*>(x_) + row * C;
+    for (int c = lane; c < C; c += 32) {
+      const float v = x[c];
+      s += v;
+      ss += v * v;
+    }
+  } else {
+    const bf16* x = reinterpret_cast<const bf16*>(x_) + row * C;
+    for (int o = lane; o < (C >> 3); o += 32) {
+      int4 raw = *reinterpret_cast<const int4*>(x + o * 8);
+      float v[8];
+      bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += v[j];
+        ss += v[j] * v[j];
+      }
+    }
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float mean = s / C;
+  float var = ss / C - mean * mean;
+  var = var < 0.f ? 0.f : var;
+  const float rstd = rsqrtf(var + eps);
+  if (F32) {
+    const float* x = reinterpret_cast<const float*>(x_) + row * C;
+    float* y = reinterpret_cast<float*>(y_) + row * C;
+    for (int c = lane; c < C; c += 32) {
+      float v = (x[c] - mean) * rstd * g[c];
+      if (bias) v += bias[c];
+      y[c] = v;
+    }
+  } else {
+    const bf16* x = reinterpret_cast<const bf16*>(x_) + row * C;
+    const bf16* res = reinterpret_cast<const bf16*>(res_);
+    bf16* y = reinterpret_cast<bf16*>(y_) + row * C;
+    for (int o = lane; o < (C >> 3); o += 32) {
+      int4 raw = *reinterpret_cast<const int4*>(x + o * 8);
+      float v[8];
+      bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = (v[j] - mean) * rstd * g[o * 8 + j];
+        if (bias) v[j] += bias[o * 8 + j];
+      }
+      if (res) {
+        int4 rr = *reinterpret_cast<const int4*>(res + row * C + o * 8);
+        float r[8];
+        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rr), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      }
+      bf16x8 o8 = float_to_bf16x8(v);
+      *reinterpret_cast<int4*>(y + o * 8) = *reinterpret_cast<int4*>(&o8);
+    }
+  }
+}
+
+int pick_nblk(long HW, int lanes, int B) {
+  // enough blocks to fill 148 SMs a few times over, but at least `lanes` pixels per block
+  long want = (long)kd_num_sms() * 4 / (B > 0 ? B : 1);
+  if (want < 1) want = 1;
+  long maxb = (HW + lanes - 1) / lanes;
+  if (want > maxb) want = maxb;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace
+
+#define KD_CHECK_OCT(C)                                                                                   \
+  KD_REQUIRE((C) > 0 && (C) % 8 == 0 && (C) / 8 <= 256, "channel count %d must be a multiple of 8 and <= 2048", (C))
+
+extern "C" int kd_gn_stats(const void* x, int B, long HW, int C, int c_offset, int group_size, int num_groups, float* partial,
+                           int nblk, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && partial && B > 0 && HW > 0 && nblk > 0, "kd_gn_stats: bad argument");
+  KD_CHECK_OCT(C);
+  KD_REQUIRE(group_size % 8 == 0 && c_offset % 8 == 0 && num_groups <= 32, "kd_gn_stats: group_size/c_offset must be multiples of 8");
+  const int T = threads_for_oct(C / 8);
+  gn_stats_kernel<<<dim3(nblk, B), T, T * 2 * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(x), HW, C, c_offset,
+                                                                        group_size, num_groups, partial, nblk);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gn_finalize(const float* partial_a, int nblk_a, float scale_a, const float* partial_b, int nblk_b, float scale_b,
+                              int B, int num_groups, double count, float eps, float* mean_rstd, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(partial_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && count > 0, "kd_gn_finalize: bad argument");
+  gn_finalize_kernel<<<B, 32, 0, stream>>>(partial_a, nblk_a, scale_a, partial_b, nblk_b, scale_b, num_groups, count, eps, mean_rstd);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int group_size, int num_groups,
+                           float src_scale, const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift,
+                           int Ctot, int act, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && y && mean_rstd && gamma && beta && B > 0 && HW > 0, "kd_gn_apply: bad argument");
+  KD_CHECK_OCT(C);
+  KD_REQUIRE(group_size % 8 == 0 && c_offset % 8 == 0, "kd_gn_apply: group_size/c_offset must be multiples of 8");
+  const int T = threads_for_oct(C / 8);
+  const int nblk = pick_nblk(HW, T / (C / 8), B);
+  gn_apply_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), HW, C, c_offset,
+                                                   group_size, num_groups, src_scale, mean_rstd, gamma, beta, scale_shift, Ctot,
+                                                   act, nblk);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_rowdot(const void* x, const float* w, const float* bias, float* out, int B, long HW, int C, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && w && out && B > 0 && HW > 0, "kd_rowdot: bad argument");
+  KD_CHECK_OCT(C);
+  const int oct = C / 8;
+  KD_REQUIRE(oct >= 32 || (oct & (oct - 1)) == 0, "kd_rowdot: C/8 = %d must be a power of two when < 32", oct);
+  const long rows = (long)B * HW;
+  const int sub = oct < 32 ? oct : 32;
+  long blocks = (rows / (32 / sub) + 7) / 8;  // 8 warps per block
+  const long cap = (long)kd_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  rowdot_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), w, bias, out, rows, C);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gca_pool(const void* x, const float* logits, int B, long HW, int C, int nblk, float* part, float* ml,
+                           kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && logits && part && ml && B > 0 && HW > 0 && nblk > 0, "kd_gca_pool: bad argument");
+  KD_CHECK_OCT(C);
+  const int T = threads_for_oct(C / 8);
+  const size_t smem = sizeof(float) * (size_t)T * 8;
+  gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const bf16*>(x), logits, HW, C, nblk, part, ml);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(part && ml && pooled && B > 0 && nblk > 0 && C > 0, "kd_gca_finalize: bad argument");
+  gca_finalize_kernel<<<dim3(kd_ceil_div(C, 128), B), 128, 0, stream>>>(part, ml, nblk, C, pooled);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, int B, long HW, int C,
+                                kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(h && out && B > 0 && HW > 0, "kd_gate_residual: bad argument");
+  KD_CHECK_OCT(C);
+  const int T = threads_for_oct(C / 8);
+  const int nblk = pick_nblk(HW, T / (C / 8), B);
+  gate_residual_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const bf16*>(h), gate, reinterpret_cast<const bf16*>(res),
+                                                        reinterpret_cast<bf16*>(out), HW, C, nblk);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_layernorm_bf16(const void* x, const float* g, const float* bias, const void* residual, void* y, long M, int C,
+                                 float eps, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && g && y && M > 0 && C > 0 && C % 8 == 0, "kd_layernorm_bf16: bad argument (C=%d)", C);
+  layernorm_kernel<false><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(x, g, bias, residual, y, M, C, eps);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_layernorm_f32(const float* x, const float* g, const float* bias, float* y, long M, int C, float eps,
+                                kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && g && y && M > 0 && C > 0, "kd_layernorm_f32: bad argument");
+  layernorm_kernel<true><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(x, g, bias, nullptr, y, M, C, eps);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}

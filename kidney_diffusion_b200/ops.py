@@ -1,0 +1,360 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point of include/kidney_b200.h).
+
+PyTorch is used only for device memory and streams: every function checks dtype / layout, allocates the output with
+``torch.empty`` and enqueues the hand-written CUDA kernel on the current stream.  Nothing here computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import KdConvDesc, check
+
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+PRED = {"noise": 0, "v": 1, "x_start": 2}
+
+launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.KdError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.KdError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.KdError(f"{name}: expected a contiguous tensor")
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def lib():
+    l = _lib.load()
+    _lib.require_b200()
+    return l
+
+
+# ------------------------------------------------------------------------------------------------ K1 conv / GEMM
+def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
+              addend=None, addend_scale=None, out=None):
+    """xa / xb: NHWC bf16 [B,H,W,C]; w: packed bf16 [Cout, taps*(Ca+Cb)]; returns NHWC (bf16 or fp32)."""
+    _chk(xa, torch.bfloat16, "xa")
+    _chk(w, torch.bfloat16, "w")
+    B, Hin, Win, Ca = xa.shape
+    Cb = 0
+    if xb is not None:
+        _chk(xb, torch.bfloat16, "xb")
+        assert xb.shape[:3] == xa.shape[:3]
+        Cb = xb.shape[3]
+    H, W = (Hin // 2, Win // 2) if mode == 1 else (Hin, Win)
+    Cout = w.shape[0]
+    taps = 4 if mode == 1 else (ksize * ksize if mode == 0 else 1)
+    assert w.shape[1] == taps * (Ca + Cb), f"weight K {w.shape[1]} != {taps}*({Ca}+{Cb})"
+    if out is None:
+        oshape = (B, 2 * H, 2 * W, Cout // 4) if out_mode == 1 else (B, H, W, Cout)
+        out = torch.empty(oshape, device=xa.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    addend_f32 = 0
+    if addend is not None:
+        assert addend.is_contiguous() and addend.shape == out.shape
+        addend_f32 = 1 if addend.dtype == torch.float32 else 0
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if addend_scale is not None:
+        _chk(addend_scale, torch.float32, "addend_scale")
+        assert addend_scale.shape == (B, Cout)
+    d = KdConvDesc(mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, 1 if out_f32 else 0, addend_f32)
+    check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
+                             _ptr(out), _stream()), "kd_conv_gemm")
+    _count()
+    return out
+
+
+def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None):
+    """Plain GEMM y[M,N] = x[M,K] @ w[N,K]^T on tensor cores (mode 2)."""
+    _chk(x, torch.bfloat16, "x")
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    d = KdConvDesc(2, 1, 1, M, K, 0, N, 1, act, 0, 1 if out_f32 else 0, 0 if addend is None or addend.dtype == torch.bfloat16 else 1)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(x), None, _ptr(w), _ptr(bias), _ptr(addend), None, _ptr(out), _stream()),
+          "kd_conv_gemm(mode 2)")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ small linear / time embedding
+def linear_small(x, w, bias=None, *, pre_act=ACT_NONE, post_act=ACT_NONE, out=None, ldy=None):
+    """fp32 y[M,N] = post(pre(x[M,K]) @ w[N,K]^T + bias); `out` may be a strided row view (ldy)."""
+    _chk(w, torch.float32, "w")
+    assert x.dtype == torch.float32 and x.is_cuda
+    M, K = x.shape
+    ldx = x.stride(0)
+    assert x.stride(1) == 1
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        ldy = N
+    elif ldy is None:
+        ldy = out.stride(0)
+    check(lib().kd_linear_small(_ptr(x), M, K, ldx, _ptr(w), _ptr(bias), _ptr(out), N, ldy, pre_act, post_act, _stream()),
+          "kd_linear_small")
+    _count()
+    return out
+
+
+def sinu_emb(t, weights):
+    _chk(t, torch.float32, "t")
+    _chk(weights, torch.float32, "weights")
+    B, half = t.shape[0], weights.shape[0]
+    out = torch.empty((B, 2 * half + 1), device=t.device, dtype=torch.float32)
+    check(lib().kd_sinu_emb(_ptr(t), _ptr(weights), B, half, _ptr(out), _stream()), "kd_sinu_emb")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+def _nblk(HW, C, B):
+    oct_ = C // 8
+    threads = 256 if oct_ >= 256 else (256 // oct_) * oct_
+    lanes = max(1, threads // oct_)
+    want = max(1, (148 * 4) // max(B, 1))
+    return int(max(1, min(want, -(-HW // lanes))))
+
+
+def gn_stats(x, c_offset, group_size, num_groups):
+    _chk(x, torch.bfloat16, "x")
+    B, H, W, C = x.shape
+    HW = H * W
+    nblk = _nblk(HW, C, B)
+    partial = torch.empty((B, nblk, num_groups, 2), device=x.device, dtype=torch.float32)
+    check(lib().kd_gn_stats(_ptr(x), B, HW, C, c_offset, group_size, num_groups, _ptr(partial), nblk, _stream()), "kd_gn_stats")
+    _count()
+    return partial
+
+
+def gn_finalize(partial_a, scale_a, partial_b, scale_b, count, eps=1e-5):
+    B, nblk_a, G, _ = partial_a.shape
+    nblk_b = 0 if partial_b is None else partial_b.shape[1]
+    mean_rstd = torch.empty((B, G, 2), device=partial_a.device, dtype=torch.float32)
+    check(lib().kd_gn_finalize(_ptr(partial_a), nblk_a, scale_a, _ptr(partial_b), nblk_b, scale_b, B, G, float(count), eps,
+                               _ptr(mean_rstd), _stream()), "kd_gn_finalize")
+    _count()
+    return mean_rstd
+
+
+def gn_apply(x, mean_rstd, gamma, beta, *, c_offset, group_size, num_groups, src_scale=1.0, scale_shift=None, ctot=None,
+             act=ACT_SILU):
+    _chk(x, torch.bfloat16, "x")
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    ctot = ctot if ctot is not None else C
+    if scale_shift is not None:
+        assert scale_shift.dtype == torch.float32 and scale_shift.stride(-1) == 1 and scale_shift.shape[-1] == 2 * ctot
+        assert scale_shift.is_contiguous()
+    check(lib().kd_gn_apply(_ptr(x), _ptr(y), B, H * W, C, c_offset, group_size, num_groups, src_scale, _ptr(mean_rstd),
+                            _ptr(gamma), _ptr(beta), _ptr(scale_shift), ctot, act, _stream()), "kd_gn_apply")
+    _count()
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ GlobalContext
+def rowdot(x, w, bias):
+    _chk(x, torch.bfloat16, "x")
+    B, H, W, C = x.shape
+    out = torch.empty((B, H * W), device=x.device, dtype=torch.float32)
+    check(lib().kd_rowdot(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), B, H * W, C, _stream()), "kd_rowdot")
+    _count()
+    return out
+
+
+def gca_pool(x, logits):
+    B, H, W, C = x.shape
+    HW = H * W
+    nblk = _nblk(HW, C, B)
+    part = torch.empty((B, nblk, C), device=x.device, dtype=torch.float32)
+    ml = torch.empty((B, nblk, 2), device=x.device, dtype=torch.float32)
+    check(lib().kd_gca_pool(_ptr(x), _ptr(logits), B, HW, C, nblk, _ptr(part), _ptr(ml), _stream()), "kd_gca_pool")
+    pooled = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    check(lib().kd_gca_finalize(_ptr(part), _ptr(ml), B, nblk, C, _ptr(pooled), _stream()), "kd_gca_finalize")
+    _count(2)
+    return pooled
+
+
+def gate_residual(h, gate, res):
+    _chk(h, torch.bfloat16, "h")
+    B, H, W, C = h.shape
+    out = torch.empty_like(h)
+    check(lib().kd_gate_residual(_ptr(h), _ptr(gate), _ptr(res), _ptr(out), B, H * W, C, _stream()), "kd_gate_residual")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def layernorm_bf16(x, g, bias=None, residual=None, eps=1e-5):
+    _chk(x, torch.bfloat16, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    check(lib().kd_layernorm_bf16(_ptr(x), _ptr(g), _ptr(bias), _ptr(residual), _ptr(y), M, C, eps, _stream()), "kd_layernorm_bf16")
+    _count()
+    return y
+
+
+def layernorm_f32(x, g, bias=None, eps=1e-5):
+    _chk(x, torch.float32, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    check(lib().kd_layernorm_f32(_ptr(x), _ptr(g), _ptr(bias), _ptr(y), M, C, eps, _stream()), "kd_layernorm_f32")
+    _count()
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def kv_assemble(qkv, kv_col, ctx_kv, null_kv):
+    """qkv: bf16 [B,N,ld]; ctx_kv: fp32 [B,Jc,128] or None; null_kv fp32 [2,64] -> bf16 [B, Jc+1+N, 128]."""
+    B, N, ld = qkv.shape
+    Jc = 0 if ctx_kv is None else ctx_kv.shape[1]
+    out = torch.empty((B, Jc + 1 + N, 128), device=qkv.device, dtype=torch.bfloat16)
+    check(lib().kd_kv_assemble(_ptr(qkv), ld, kv_col, _ptr(ctx_kv), Jc, _ptr(null_kv), _ptr(out), B, N, _stream()), "kd_kv_assemble")
+    _count()
+    return out
+
+
+def attn_mqa(q, kv, heads, scale):
+    """q: bf16 [B,N,ld] (first heads*64 columns are the queries); kv: bf16 [B,J,128]."""
+    B, N, ld = q.shape
+    J = kv.shape[1]
+    out = torch.empty((B, N, heads * 64), device=q.device, dtype=torch.bfloat16)
+    check(lib().kd_attn_mqa(_ptr(q), ld, _ptr(kv), _ptr(out), B, N, J, heads, scale, _stream()), "kd_attn_mqa")
+    _count()
+    return out
+
+
+def attn_cross(q, kv, null_kv, heads, scale):
+    """q: bf16 [B,N,heads*64]; kv: fp32 [B,Jc,2*heads*64]; null_kv fp32 [2,64]."""
+    B, N, ld = q.shape
+    Jc = kv.shape[1]
+    out = torch.empty((B, N, heads * 64), device=q.device, dtype=torch.bfloat16)
+    check(lib().kd_attn_cross(_ptr(q), ld, _ptr(kv), _ptr(null_kv), _ptr(out), B, N, Jc, heads, scale, _stream()), "kd_attn_cross")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ edge convs
+def im2col_nchw(x, ksize, Kp):
+    _chk(x, torch.float32, "x")
+    B, C, H, W = x.shape
+    out = torch.empty((B * H * W, Kp), device=x.device, dtype=torch.bfloat16)
+    check(lib().kd_im2col_nchw(_ptr(x), B, C, H, W, ksize, _ptr(out), Kp, _stream()), "kd_im2col_nchw")
+    _count()
+    return out
+
+
+def final_conv(xa, xb, w, bias):
+    """xa: NHWC bf16; xb: NCHW fp32 or None; w: fp32 [Cout,3,3,Ca+Cb] -> NCHW fp32 [B,Cout,H,W]."""
+    _chk(xa, torch.bfloat16, "xa")
+    B, H, W, Ca = xa.shape
+    Cb = 0 if xb is None else xb.shape[1]
+    Cout = w.shape[0]
+    out = torch.empty((B, Cout, H, W), device=xa.device, dtype=torch.float32)
+    check(lib().kd_final_conv(_ptr(xa), Ca, _ptr(xb), Cb, _ptr(w), _ptr(bias), _ptr(out), B, H, W, Cout, _stream()), "kd_final_conv")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ sampler update
+def quantile_ranks(n, q=0.95):
+    """Mirror of ATen quantile_compute (linear interpolation): ranks = q * (n - 1) evaluated in float32."""
+    rank = torch.tensor(q, dtype=torch.float32) * (n - 1)
+    lo = rank.floor()
+    weight = float(rank - lo)
+    hi = int(rank.ceil().item())
+    return int(lo.item()), hi, weight
+
+
+def dynthresh(x_t, pred, objective, alpha, sigma, q=0.95, workspace=None):
+    _chk(x_t, torch.float32, "x_t")
+    _chk(pred, torch.float32, "pred")
+    B = x_t.shape[0]
+    n_per = x_t[0].numel()
+    lo, hi, weight = quantile_ranks(n_per, q)
+    nbytes = lib().kd_dynthresh_workspace_bytes(B)
+    if workspace is None:
+        workspace = torch.empty(nbytes, device=x_t.device, dtype=torch.uint8)
+    s = torch.empty((B,), device=x_t.device, dtype=torch.float32)
+    check(lib().kd_dynthresh(_ptr(x_t), _ptr(pred), B, n_per, PRED[objective], alpha, sigma, lo, hi, weight, _ptr(workspace), nbytes,
+                             _ptr(s), _stream()), "kd_dynthresh")
+    _count(10)
+    return s
+
+
+def ddpm_step(x_t, pred, noise, s, objective, sc, *, renoise=None, rn=(0.0, 0.0, 1.0), out=None, x0_out=None):
+    """sc: dict of fp32 python floats alpha, sigma, one_minus_c, c, alpha_next, std."""
+    _chk(x_t, torch.float32, "x_t")
+    B = x_t.shape[0]
+    n_per = x_t[0].numel()
+    if out is None:
+        out = torch.empty_like(x_t)
+    check(lib().kd_ddpm_step(_ptr(x_t), _ptr(pred), _ptr(noise), _ptr(s), _ptr(out), _ptr(x0_out), B, n_per, PRED[objective],
+                             sc["alpha"], sc["sigma"], sc["one_minus_c"], sc["c"], sc["alpha_next"], sc["std"], _ptr(renoise),
+                             rn[0], rn[1], rn[2], _stream()), "kd_ddpm_step")
+    _count()
+    return out
+
+
+def inpaint_blend(img, inpaint, mask, noise, alpha, sigma):
+    B, C, H, W = img.shape
+    _chk(mask, torch.uint8, "mask")
+    check(lib().kd_inpaint_blend(_ptr(img), _ptr(inpaint), _ptr(mask), _ptr(noise), alpha, sigma, B, C, H * W, _stream()),
+          "kd_inpaint_blend")
+    _count()
+    return img
+
+
+def finalize_image(img, inpaint=None, mask=None):
+    B, C, H, W = img.shape
+    check(lib().kd_finalize_image(_ptr(img), _ptr(inpaint), _ptr(mask), B, C, H * W, _stream()), "kd_finalize_image")
+    _count()
+    return img
+
+
+def q_sample(x0, noise, alpha, sigma):
+    out = torch.empty_like(x0)
+    check(lib().kd_q_sample(_ptr(x0), _ptr(noise), alpha, sigma, _ptr(out), x0.numel(), _stream()), "kd_q_sample")
+    _count()
+    return out
+
+
+def randn(shape, seed, key, device):
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    check(lib().kd_randn(_ptr(out), out.numel(), seed & (2**64 - 1), key & (2**64 - 1), _stream()), "kd_randn")
+    _count()
+    return out
+
+
+def border_pack(S, overlap_pos, orientation, above, side, corner, device):
+    inpaint = torch.empty((3, S, S), device=device, dtype=torch.float32)
+    mask = torch.empty((S, S), device=device, dtype=torch.uint8)
+    check(lib().kd_border_pack(_ptr(inpaint), _ptr(mask), _ptr(above), _ptr(side), _ptr(corner), S, overlap_pos, orientation,
+                               _stream()), "kd_border_pack")
+    _count()
+    return inpaint, mask

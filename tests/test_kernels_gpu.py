@@ -1,0 +1,479 @@
+"""Parity of every CUDA entry point (called through the C ABI) against a plain PyTorch fp32 CPU restatement of the
+same reference operation (oracle/imagen_oracle.py for module-level math).
+
+Tolerances: bf16 tensor-core kernels rel-L2 <= 1e-2 (north_star), typically ~3e-3 from operand rounding;
+fp32 elementwise / sampler kernels bit-exact or <= 1e-6 where transcendental functions differ.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16 on device
+    return bf(x.permute(0, 2, 3, 1).contiguous()).to(DEV)
+
+
+def from_nhwc(y):
+    return y.float().cpu().permute(0, 3, 1, 2)
+
+
+def pack_w(w):  # [Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] bf16
+    return bf(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()).to(DEV)
+
+
+def rb(x):  # round-trip through bf16 so the reference sees the same operand values
+    return x.to(torch.bfloat16).float()
+
+
+# ------------------------------------------------------------------------------------------------ conv_gemm
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k
+    (1, 16, 16, 64, 128, 3),
+    (2, 32, 32, 128, 128, 3),
+    (1, 64, 64, 256, 256, 3),
+    (3, 8, 8, 128, 64, 3),       # tile spans two images, batch tail
+    (1, 24, 40, 64, 192, 3),     # non power-of-two spatial size -> partial tiles, Cout not a multiple of 128
+    (2, 16, 16, 192, 128, 1),
+    (1, 4, 4, 64, 128, 3),       # tiny spatial
+    (1, 32, 32, 1024, 128, 3),   # long K loop (144 k-blocks): ring wrap-around many times
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", CONV_CASES)
+def test_conv_gemm_matches_conv2d(cuda_lib, B, H, W, Cin, Cout, k):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + k)
+    x = rb(torch.randn(B, Cin, H, W, generator=g))
+    w = rb(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    out = ops.conv_gemm(nhwc(x), pack_w(w), b.to(DEV), ksize=k)
+    torch.cuda.synchronize()
+    err = rel_l2(from_nhwc(out), ref)
+    print(f"conv {B}x{H}x{W} {Cin}->{Cout} k{k}: rel_l2={err:.3e}")
+    assert err < 5e-3
+
+
+def test_conv_gemm_two_sources_act_addend_gate(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    B, H, W, Ca, Cb, Cout = 2, 16, 16, 128, 64, 128
+    xa, xb = rb(torch.randn(B, Ca, H, W, generator=g)), rb(torch.randn(B, Cb, H, W, generator=g))
+    w = rb(torch.randn(Cout, Ca + Cb, 3, 3, generator=g) / math.sqrt((Ca + Cb) * 9))
+    b = torch.randn(Cout, generator=g)
+    add = rb(torch.randn(B, Cout, H, W, generator=g))
+    gate = torch.rand(B, Cout, generator=g)
+    ref = F.silu(F.conv2d(torch.cat((xa, xb), 1), w, b, padding=1)) + gate[:, :, None, None] * add
+    out = ops.conv_gemm(nhwc(xa), pack_w(w), b.to(DEV), xb=nhwc(xb), ksize=3, act=ops.ACT_SILU, addend=nhwc(add),
+                        addend_scale=gate.to(DEV))
+    err = rel_l2(from_nhwc(out), ref)
+    print("two-source conv rel_l2", err)
+    assert err < 5e-3
+    # fp32 output + fp32 addend, GELU
+    ref2 = F.gelu(F.conv2d(torch.cat((xa, xb), 1), w, b, padding=1)) + add
+    out2 = ops.conv_gemm(nhwc(xa), pack_w(w), b.to(DEV), xb=nhwc(xb), ksize=3, act=ops.ACT_GELU, out_f32=True,
+                         addend=add.permute(0, 2, 3, 1).contiguous().to(DEV))
+    assert out2.dtype == torch.float32
+    err2 = rel_l2(out2.cpu().permute(0, 3, 1, 2), ref2)
+    print("fp32-out conv rel_l2", err2)
+    assert err2 < 5e-3
+
+
+def test_conv_gemm_downsample_mode(cuda_lib):
+    """Downsample = 'b c (h 2) (w 2) -> b (c 2 2) h w' + Conv2d(4c, cout, 1)."""
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import Downsample
+
+    torch.manual_seed(3)
+    C, Cout = 64, 128
+    mod = Downsample(C, Cout)
+    x = rb(torch.randn(2, C, 32, 32))
+    with torch.no_grad():
+        mod[1].weight.copy_(rb(mod[1].weight))
+        ref = mod(x)
+    w = mod[1].weight.detach().view(Cout, C, 2, 2)  # input channel index = c*4 + dy*2 + dx
+    wp = bf(w.permute(0, 2, 3, 1).reshape(Cout, 4 * C).contiguous()).to(DEV)  # k = (dy*2+dx)*C + c
+    out = ops.conv_gemm(nhwc(x), wp, mod[1].bias.detach().to(DEV), mode=1)
+    assert out.shape == (2, 16, 16, Cout)
+    err = rel_l2(from_nhwc(out), ref)
+    print("downsample rel_l2", err)
+    assert err < 5e-3
+
+
+def test_conv_gemm_pixel_shuffle_mode(cuda_lib):
+    """PixelShuffleUpsample = Conv2d(c, 4*cout, 1) -> SiLU -> PixelShuffle(2)."""
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import PixelShuffleUpsample
+
+    torch.manual_seed(4)
+    C, Cout = 128, 64
+    mod = PixelShuffleUpsample(C, Cout)
+    conv = mod.net[0]
+    with torch.no_grad():
+        conv.weight.copy_(rb(torch.randn_like(conv.weight) / math.sqrt(C)))
+        conv.bias.copy_(torch.randn_like(conv.bias))
+    x = rb(torch.randn(2, C, 16, 16))
+    with torch.no_grad():
+        ref = mod(x)
+    w = conv.weight.detach().view(Cout, 4, C)  # out channel = c*4 + (dy*2+dx)
+    wp = bf(w.permute(1, 0, 2).reshape(4 * Cout, C).contiguous()).to(DEV)  # rows ordered (dy*2+dx, c)
+    bp = conv.bias.detach().view(Cout, 4).t().reshape(-1).contiguous().to(DEV)
+    out = ops.conv_gemm(nhwc(x), wp, bp, ksize=1, act=ops.ACT_SILU, out_mode=1)
+    assert out.shape == (2, 32, 32, Cout)
+    err = rel_l2(from_nhwc(out), ref)
+    print("pixel-shuffle rel_l2", err)
+    assert err < 5e-3
+
+
+def test_gemm_rows(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 300, 704, 128
+    x, w, b = rb(torch.randn(M, K, generator=g)), rb(torch.randn(N, K, generator=g) / math.sqrt(K)), torch.randn(N, generator=g)
+    out = ops.gemm_rows(bf(x).to(DEV), bf(w).to(DEV), b.to(DEV), out_f32=True)
+    err = rel_l2(out, x @ w.t() + b)
+    print("gemm_rows rel_l2", err)
+    assert err < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ conditioning towers
+def test_linear_small_and_sinu(cuda_lib):
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import LearnedSinusoidalPosEmb
+
+    g = torch.Generator().manual_seed(6)
+    for M, K, N in [(4, 17, 512), (3, 1024, 2048), (20, 512, 1024), (1, 64, 3)]:
+        x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+        ref = F.silu(F.linear(F.silu(x), w, b))
+        out = ops.linear_small(x.to(DEV), w.to(DEV), b.to(DEV), pre_act=ops.ACT_SILU, post_act=ops.ACT_SILU)
+        err = rel_l2(out, ref)
+        assert err < 1e-5, (M, K, N, err)
+    torch.manual_seed(1)
+    emb = LearnedSinusoidalPosEmb(16)
+    t = torch.tensor([8.7692, 2.18, -0.0249, -33.891])
+    ref = emb(t).detach()
+    out = ops.sinu_emb(t.to(DEV), emb.weights.detach().to(DEV))
+    assert float((out.cpu() - ref).abs().max()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+@pytest.mark.parametrize("B,H,W,Ca,Cb", [(2, 16, 16, 128, 0), (1, 32, 32, 256, 128), (2, 8, 8, 1024, 512), (1, 64, 64, 64, 64)])
+def test_groupnorm_scale_shift_silu(cuda_lib, B, H, W, Ca, Cb):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(Ca + Cb + H)
+    C, G = Ca + Cb, 8
+    skip_scale = 2 ** -0.5
+    xa = rb(torch.randn(B, Ca, H, W, generator=g) * 2 + 0.5)
+    xb = rb(torch.randn(B, Cb, H, W, generator=g)) if Cb else None
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ss = torch.randn(B, 2 * C, generator=g) * 0.3
+    x = xa if xb is None else torch.cat((xa, xb * skip_scale), 1)
+    scale, shift = ss[:, :C, None, None], ss[:, C:, None, None]
+    ref = F.silu(F.group_norm(x, G, gamma, beta, eps=1e-5) * (scale + 1) + shift)
+    gs = C // G
+    da = nhwc(xa)
+    pa = ops.gn_stats(da, 0, gs, G)
+    pb, db = None, None
+    if xb is not None:
+        db = nhwc(xb)
+        pb = ops.gn_stats(db, Ca, gs, G)
+    mr = ops.gn_finalize(pa, 1.0, pb, skip_scale, count=gs * H * W)
+    kw = dict(group_size=gs, num_groups=G, scale_shift=ss.to(DEV), ctot=C)
+    ya = ops.gn_apply(da, mr, gamma.to(DEV), beta.to(DEV), c_offset=0, **kw)
+    out = from_nhwc(ya)
+    if xb is not None:
+        yb = ops.gn_apply(db, mr, gamma.to(DEV), beta.to(DEV), c_offset=Ca, src_scale=skip_scale, **kw)
+        out = torch.cat((out, from_nhwc(yb)), 1)
+    err = rel_l2(out, ref)
+    print("groupnorm rel_l2", err)
+    assert err < 4e-3  # bf16 output rounding
+
+
+# ------------------------------------------------------------------------------------------------ GlobalContext
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 64, 64, 256), (2, 8, 8, 1024), (1, 128, 128, 128)])
+def test_global_context_gate_residual(cuda_lib, B, H, W, C):
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import GlobalContext
+
+    torch.manual_seed(C + H)
+    gca = GlobalContext(dim_in=C, dim_out=C)
+    with torch.no_grad():
+        gca.to_k.weight.mul_(4.0)  # sharper softmax
+    x = rb(torch.randn(B, C, H, W))
+    res = rb(torch.randn(B, C, H, W))
+    with torch.no_grad():
+        gate_ref = gca(x)
+        ref = x * gate_ref + res
+    dx = nhwc(x)
+    logits = ops.rowdot(dx, gca.to_k.weight.detach().view(C).to(DEV), gca.to_k.bias.detach().to(DEV))
+    pooled = ops.gca_pool(dx, logits)
+    hid = ops.linear_small(pooled, gca.net[0].weight.detach().view(-1, C).to(DEV), gca.net[0].bias.detach().to(DEV), post_act=ops.ACT_SILU)
+    gate = ops.linear_small(hid, gca.net[2].weight.detach().view(C, -1).to(DEV), gca.net[2].bias.detach().to(DEV), post_act=ops.ACT_SIGMOID)
+    e_gate = rel_l2(gate, gate_ref.view(B, C))
+    out = ops.gate_residual(dx, gate, nhwc(res))
+    err = rel_l2(from_nhwc(out), ref)
+    print("gca gate rel_l2", e_gate, "out", err)
+    assert e_gate < 1e-4 and err < 4e-3
+
+
+def test_layernorm(cuda_lib):
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import LayerNorm
+
+    torch.manual_seed(2)
+    for M, C in [(100, 128), (4096, 1024), (7, 2048)]:
+        ln = LayerNorm(C)
+        with torch.no_grad():
+            ln.g.copy_(torch.randn(C))
+        x, r = rb(torch.randn(M, C) * 3 + 1), rb(torch.randn(M, C))
+        ref = ln(x).detach() + r
+        out = ops.layernorm_bf16(bf(x).to(DEV), ln.g.detach().to(DEV), None, bf(r).to(DEV))
+        assert rel_l2(out, ref) < 4e-3
+    nl = torch.nn.LayerNorm(512)
+    with torch.no_grad():
+        nl.weight.copy_(torch.randn(512)); nl.bias.copy_(torch.randn(512))
+    x = torch.randn(12, 512)
+    out = ops.layernorm_f32(x.to(DEV), nl.weight.detach().to(DEV), nl.bias.detach().to(DEV))
+    assert rel_l2(out, nl(x).detach()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,N,Jc", [(2, 256, 0), (1, 1024, 4), (2, 100, 36), (1, 4096, 0)])
+def test_attn_mqa(cuda_lib, B, N, Jc):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(N + Jc)
+    heads, d = 8, 64
+    qkv = rb(torch.randn(B, N, heads * d + 2 * d, generator=g))
+    ctx = torch.randn(B, Jc, 2 * d, generator=g) if Jc else None
+    null_kv = torch.randn(2, d, generator=g)
+    q = qkv[..., : heads * d].view(B, N, heads, d).transpose(1, 2) * d ** -0.5
+    k, v = qkv[..., heads * d: heads * d + d], qkv[..., heads * d + d:]
+    k = torch.cat((rb(null_kv[0]).expand(B, 1, d), k), 1)
+    v = torch.cat((rb(null_kv[1]).expand(B, 1, d), v), 1)
+    if Jc:
+        k = torch.cat((rb(ctx[..., :d]), k), 1)
+        v = torch.cat((rb(ctx[..., d:]), v), 1)
+    attn = torch.einsum("bhid,bjd->bhij", q, k).softmax(-1)
+    ref = torch.einsum("bhij,bjd->bhid", attn, v).transpose(1, 2).reshape(B, N, heads * d)
+    dq = bf(qkv).to(DEV)
+    kv = ops.kv_assemble(dq, heads * d, None if ctx is None else ctx.to(DEV), null_kv.to(DEV))
+    assert kv.shape == (B, Jc + 1 + N, 128)
+    out = ops.attn_mqa(dq, kv, heads, d ** -0.5)
+    err = rel_l2(out, ref)
+    print("attn_mqa rel_l2", err)
+    assert err < 8e-3
+
+
+@pytest.mark.parametrize("B,N,Jc", [(2, 256, 4), (1, 4096, 4), (1, 70, 40)])
+def test_attn_cross(cuda_lib, B, N, Jc):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(N * 3 + Jc)
+    heads, d = 8, 64
+    q = rb(torch.randn(B, N, heads * d, generator=g))
+    kv = torch.randn(B, Jc, 2 * heads * d, generator=g)
+    null_kv = torch.randn(2, d, generator=g)
+    qh = q.view(B, N, heads, d).transpose(1, 2) * d ** -0.5
+    k = kv[..., : heads * d].view(B, Jc, heads, d).transpose(1, 2)
+    v = kv[..., heads * d:].view(B, Jc, heads, d).transpose(1, 2)
+    k = torch.cat((null_kv[0].expand(B, heads, 1, d), k), 2)
+    v = torch.cat((null_kv[1].expand(B, heads, 1, d), v), 2)
+    ref = (torch.einsum("bhid,bhjd->bhij", qh, k).softmax(-1) @ v).transpose(1, 2).reshape(B, N, heads * d)
+    out = ops.attn_cross(bf(q).to(DEV), kv.to(DEV), null_kv.to(DEV), heads, d ** -0.5)
+    err = rel_l2(out, ref)
+    print("attn_cross rel_l2", err)
+    assert err < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ edge convs
+def test_im2col_and_cross_embed(cuda_lib):
+    """CrossEmbedLayer(k=3,7,15) == im2col(15) @ merged 15x15 weight."""
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import CrossEmbedLayer
+
+    torch.manual_seed(8)
+    Cin, dim = 3, 128
+    mod = CrossEmbedLayer(Cin, kernel_sizes=(3, 7, 15), dim_out=dim, stride=1)
+    x = rb(torch.randn(2, Cin, 40, 72))
+    Wm = torch.zeros(dim, 15, 15, Cin)
+    bias = torch.zeros(dim)
+    o = 0
+    with torch.no_grad():
+        for conv in mod.convs:
+            conv.weight.copy_(rb(conv.weight))
+            k, co = conv.kernel_size[0], conv.out_channels
+            off = (15 - k) // 2
+            Wm[o:o + co, off:off + k, off:off + k, :] = conv.weight.permute(0, 2, 3, 1)
+            bias[o:o + co] = conv.bias
+            o += co
+        ref = mod(x)
+    Kp = ((15 * 15 * Cin + 63) // 64) * 64
+    Wp = torch.zeros(dim, Kp)
+    Wp[:, : 15 * 15 * Cin] = Wm.reshape(dim, -1)
+    panel = ops.im2col_nchw(x.to(DEV), 15, Kp)
+    # spot check the panel itself (exact)
+    unf = F.unfold(x, 15, padding=7).view(2, Cin, 225, -1).permute(0, 3, 2, 1).reshape(2 * 40 * 72, 225 * Cin)
+    assert torch.equal(panel[:, : 225 * Cin].float().cpu(), unf)
+    assert float(panel[:, 225 * Cin:].float().abs().max()) == 0.0
+    out = ops.gemm_rows(panel, bf(Wp).to(DEV), bias.to(DEV)).view(2, 40, 72, dim)
+    err = rel_l2(from_nhwc(out), ref)
+    print("cross-embed rel_l2", err)
+    assert err < 5e-3
+
+
+def test_final_conv(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(9)
+    B, H, W, Ca, Cb = 2, 40, 72, 128, 3
+    xa, xb = rb(torch.randn(B, Ca, H, W, generator=g)), torch.randn(B, Cb, H, W, generator=g)
+    w, b = torch.randn(3, Ca + Cb, 3, 3, generator=g) * 0.05, torch.randn(3, generator=g)
+    ref = F.conv2d(torch.cat((xa, xb), 1), w, b, padding=1)
+    out = ops.final_conv(nhwc(xa), xb.to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV))
+    err = rel_l2(out, ref)
+    print("final_conv rel_l2", err)
+    assert err < 1e-5
+    out2 = ops.final_conv(nhwc(xa), None, w[:, :Ca].permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV))
+    assert rel_l2(out2, F.conv2d(xa, w[:, :Ca], b, padding=1)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ sampler update (K6 / K7)
+def _sched_scalars(sched, t, t_next):
+    from kidney_diffusion_b200.schedule import step_scalars
+
+    return step_scalars(sched, t, t_next)
+
+
+@pytest.mark.parametrize("objective", ["noise", "v"])
+@pytest.mark.parametrize("n_side", [16, 64, 250])
+def test_dynthresh_and_ddpm_step_exact(cuda_lib, objective, n_side):
+    """K7 radix-select == torch.quantile bit for bit; K6 == oracle p_sample bit for bit (same fp32 expression order)."""
+    from kidney_diffusion_b200 import ops
+    from kidney_diffusion_b200.schedule import step_scalars
+    from oracle.imagen_oracle import GaussianDiffusionContinuousTimes, Imagen, NullUnet
+
+    g = torch.Generator().manual_seed(n_side)
+    B = 3
+    sched = GaussianDiffusionContinuousTimes(noise_schedule="cosine", timesteps=100)
+    x = torch.randn(B, 3, n_side, n_side, generator=g)
+    pred = torch.randn(B, 3, n_side, n_side, generator=g) * 1.7
+    noise = torch.randn(B, 3, n_side, n_side, generator=g)
+    for t, t_next in [(1.0, 0.99), (0.5, 0.49), (0.01, 0.0)]:
+        tt, tn = torch.full((B,), t), torch.full((B,), t_next)
+        # oracle
+        if objective == "noise":
+            x0 = sched.predict_start_from_noise(x, tt, pred)
+        else:
+            x0 = sched.predict_start_from_v(x, tt, pred)
+        s_ref = torch.quantile(x0.flatten(1).abs(), 0.95, dim=-1).clamp(min=1.0)
+        x0c = x0.clamp(-s_ref.view(B, 1, 1, 1), s_ref.view(B, 1, 1, 1)) / s_ref.view(B, 1, 1, 1)
+        mean, _, logvar = sched.q_posterior(x0c, x, tt, t_next=tn)
+        nonzero = (1 - (tn == 0).float()).view(B, 1, 1, 1)
+        ref = mean + nonzero * (0.5 * logvar).exp() * noise
+        # device
+        sc = step_scalars("cosine", t, t_next)
+        s = ops.dynthresh(x.to(DEV), pred.to(DEV), objective, sc["alpha"], sc["sigma"])
+        x0_out = torch.empty_like(x, device=DEV)
+        out = ops.ddpm_step(x.to(DEV), pred.to(DEV), noise.to(DEV), s, objective, sc, x0_out=x0_out)
+        torch.cuda.synchronize()
+        assert torch.equal(s.cpu(), s_ref), (s.cpu(), s_ref)
+        assert torch.equal(x0_out.cpu(), x0c)
+        md = float((out.cpu() - ref).abs().max())
+        assert md <= 1e-6 * float(ref.abs().max()), md
+
+
+def test_dynthresh_duplicates_and_full_size(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 1024, 1024, generator=g)
+    x[0, :, :512] = 0.25  # massive duplicates
+    pred = torch.zeros_like(x)
+    # objective x_start -> x0 = pred; use v with alpha=1, sigma=0 to get x0 = x
+    s = ops.dynthresh(x.to(DEV), pred.to(DEV), "v", 1.0, 0.0)
+    ref = torch.quantile(x.flatten(1).abs(), 0.95, dim=-1).clamp(min=1.0)
+    assert torch.equal(s.cpu(), ref), (s.cpu(), ref)
+
+
+def test_inpaint_blend_finalize_qsample(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    B, S = 2, 64
+    img, inp, noise = (torch.randn(B, 3, S, S, generator=g) for _ in range(3))
+    mask = torch.rand(B, S, S, generator=g) > 0.5
+    alpha, sigma = 0.8186915, 0.5742431
+    m4 = mask[:, None]
+    ref = img * ~m4 + (alpha * inp + sigma * noise) * m4
+    out = ops.inpaint_blend(img.clone().to(DEV), inp.to(DEV), mask.to(torch.uint8).to(DEV), noise.to(DEV), alpha, sigma)
+    assert torch.equal(out.cpu(), ref)
+    ref2 = (img.clamp(-1, 1) * ~m4 + inp * m4 + 1) * 0.5
+    out2 = ops.finalize_image(img.clone().to(DEV), inp.to(DEV), mask.to(torch.uint8).to(DEV))
+    assert torch.equal(out2.cpu(), ref2)
+    out3 = ops.finalize_image(img.clone().to(DEV))
+    assert torch.equal(out3.cpu(), (img.clamp(-1, 1) + 1) * 0.5)
+    out4 = ops.q_sample(inp.to(DEV), noise.to(DEV), alpha, sigma)
+    assert torch.equal(out4.cpu(), alpha * inp + sigma * noise)
+
+
+def test_randn_statistics_and_determinism(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    a = ops.randn((3, 1024, 1024), 1234, 77, DEV)
+    b = ops.randn((3, 1024, 1024), 1234, 77, DEV)
+    c = ops.randn((3, 1024, 1024), 1234, 78, DEV)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(float(a.mean())) < 3e-3 and abs(float(a.std()) - 1) < 3e-3
+    assert abs(float((a ** 4).mean()) - 3.0) < 0.05  # kurtosis of N(0,1)
+    assert abs(float((a.flatten()[:-1] * a.flatten()[1:]).mean())) < 3e-3
+
+
+@pytest.mark.parametrize("orientation", [-1, 1])
+def test_border_pack_matches_reference_layout(cuda_lib, orientation):
+    """Restates sample_ultra_res.py:149-170 on the CPU and compares bit-exactly."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(12)
+    S, ov = 64, 16
+    above, side, corner = (torch.rand(3, S, S, generator=g) for _ in range(3))
+    for use in [(1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 0), (1, 1, 0)]:
+        a, n, c = (t if u else None for t, u in zip((above, side, corner), use))
+        ip, im = torch.zeros(3, S, S), torch.zeros(S, S)
+        if a is not None:
+            ip[:, :ov, :] = a[:, -ov:, :]
+            im[:ov, :] = 1
+        if n is not None:
+            if orientation == -1:
+                ip[:, :, :ov] = n[:, :, -ov:]
+                im[:, :ov] = 1
+            else:
+                ip[:, :, -ov:] = n[:, :, :ov]
+                im[:, -ov:] = 1
+        if c is not None:
+            if orientation == -1:
+                ip[:, :ov, :ov] = c[:, -ov:, -ov:]
+            else:
+                ip[:, :ov, -ov:] = c[:, -ov:, :ov]
+        dev = lambda t: None if t is None else t.to(DEV)
+        op, om = ops.border_pack(S, ov, orientation, dev(a), dev(n), dev(c), DEV)
+        assert torch.equal(op.cpu(), ip) and torch.equal(om.cpu().float(), im)
