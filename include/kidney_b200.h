@@ -99,10 +99,11 @@ int kd_gn_finalize(const float* partial_a, int nblk_a, float scale_a, const floa
                    int num_groups, double count /* elements per (b, group) */, float eps, float* mean_rstd /* [B][G][2] */,
                    kd_stream_t stream);
 /* y = act( ((x*src_scale - mean) * rstd * gamma + beta) * (scale + 1) + shift ), bf16 out.
- * scale_shift: [B][2*Ctot] fp32 laid out as time_mlp output (scale = first Ctot, shift = last Ctot) or NULL. */
+ * scale_shift: fp32 rows of 2*Ctot values laid out as time_mlp output (scale = first Ctot, shift = last Ctot), row b at
+ * scale_shift + b*ss_stride (so one launch of kd_linear_small can produce every block's time_mlp at once), or NULL. */
 int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int group_size, int num_groups, float src_scale,
-                const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift, int Ctot, int act,
-                kd_stream_t stream);
+                const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift, long ss_stride,
+                int Ctot, int act, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ K4: GlobalContext gate
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */

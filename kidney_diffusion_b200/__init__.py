@@ -4,3 +4,7 @@ Python host code (this package) mirrors the reference's imagen-pytorch API for t
 hand-written CUDA through the C ABI of libkidney_b200.so (include/kidney_b200.h).  No CPU fallback exists.
 """
 __version__ = "0.1.0"
+
+from .imagen import Imagen  # noqa: E402,F401
+from .trainer import ImagenTrainer, restore_parts  # noqa: E402,F401
+from .unet import NullUnet, Unet  # noqa: E402,F401

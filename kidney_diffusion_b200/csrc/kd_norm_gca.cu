@@ -83,8 +83,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ pa, int nblk_a, flo
 
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long HW, int C, int c_offset, int group_size,
                                 int G, float src_scale, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ scale_shift, int Ctot, int act,
-                                int nblk) {
+                                const float* __restrict__ beta, const float* __restrict__ scale_shift, long ss_stride, int Ctot,
+                                int act, int nblk) {
   const int oct = C >> 3;
   const int lanes = blockDim.x / oct;
   const int o = threadIdx.x % oct;
@@ -100,8 +100,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
     const float ga = gamma[cg + j], be = beta[cg + j];
     float a = rstd * ga, c = be - mean * rstd * ga;
     if (scale_shift != nullptr) {
-      const float sc = scale_shift[(long)b * 2 * Ctot + cg + j] + 1.0f;
-      const float sh = scale_shift[(long)b * 2 * Ctot + Ctot + cg + j];
+      const float sc = scale_shift[(long)b * ss_stride + cg + j] + 1.0f;
+      const float sh = scale_shift[(long)b * ss_stride + Ctot + cg + j];
       a *= sc;
       c = c * sc + sh;
     }
@@ -373,7 +373,7 @@ extern "C" int kd_gn_finalize(const float* partial_a, int nblk_a, float scale_a,
 
 extern "C" int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int group_size, int num_groups,
                            float src_scale, const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift,
-                           int Ctot, int act, kd_stream_t stream_) {
+                           long ss_stride, int Ctot, int act, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(x && y && mean_rstd && gamma && beta && B > 0 && HW > 0, "kd_gn_apply: bad argument");
   KD_CHECK_OCT(C);
@@ -381,8 +381,8 @@ extern "C" int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_
   const int T = threads_for_oct(C / 8);
   const int nblk = pick_nblk(HW, T / (C / 8), B);
   gn_apply_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), HW, C, c_offset,
-                                                   group_size, num_groups, src_scale, mean_rstd, gamma, beta, scale_shift, Ctot,
-                                                   act, nblk);
+                                                   group_size, num_groups, src_scale, mean_rstd, gamma, beta, scale_shift, ss_stride,
+                                                   Ctot, act, nblk);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

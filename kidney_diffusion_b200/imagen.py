@@ -1,0 +1,297 @@
+"""Drop-in ``Imagen`` for the sampling path (imagen-pytorch 1.18.5 ``Imagen.sample -> p_sample_loop -> p_sample ->
+p_mean_variance``; reference call sites sample_ultra_res.py:183-195, sample_cond.py:40-48, sample_uncond.py:49-55,
+construction train_ultra_res_v_param.py:78-92 / train.py:83-95 / train_uncond.py:79-93).
+
+Host side only orchestrates: per step it launches the UNet (a captured CUDA graph of hand-written kernels), the exact
+dynamic-threshold select (K7) and the fused p_sample update (K6).  Training (``forward`` / loss) is out of scope.
+"""
+from __future__ import annotations
+
+import zlib
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops, schedule
+from .modules import cast_tuple, default, exists
+from .unet import NullUnet, Unet
+
+SITES = {"lowres_aug": 1, "init": 2, "inpaint": 3, "p_sample": 4, "renoise": 5}
+
+
+def pad_tuple_to_length(t, length, fillvalue=None):
+    remain = length - len(t)
+    return t if remain <= 0 else (*t, *((fillvalue,) * remain))
+
+
+def resize_image_to(image, target_image_size, mode="nearest"):
+    if image.shape[-1] == target_image_size:
+        return image
+    return F.interpolate(image, target_image_size, mode=mode)
+
+
+class NoiseSchedulerSpec(nn.Module):
+    """Parameter-free stand-in for GaussianDiffusionContinuousTimes (keeps Imagen's module tree shape)."""
+
+    def __init__(self, *, noise_schedule, timesteps=1000):
+        super().__init__()
+        assert noise_schedule in schedule.LOG_SNR, f"invalid noise schedule {noise_schedule}"
+        self.noise_schedule = noise_schedule
+        self.num_timesteps = timesteps
+
+
+class CounterNoise:
+    """Counter-based noise: every randn site of the sampler is keyed by (seed, stream key, unet, step, r, site), so
+    results are identical for any GPU count / patch-to-rank assignment (SURVEY.md section 8e invariance requirement).
+    The reference draws from the unseeded global torch generator; tests inject identical tensors into both paths."""
+
+    def __init__(self, seed=0, stream_key=0):
+        self.seed, self.stream_key = seed, stream_key
+
+    def __call__(self, site, shape, device, unet=0, step=0, r=0):
+        key = zlib.crc32(f"{self.stream_key}/{unet}/{step}/{r}/{SITES[site]}".encode()) | (SITES[site] << 40) | (unet << 48)
+        return ops.randn(shape, self.seed, key, device)
+
+
+class _StepGraph:
+    """One UNet forward for fixed (B, S) captured as a CUDA graph (~800 kernel launches per step otherwise)."""
+
+    def __init__(self, ex, B, S, channels, lowres_t, device):
+        self.x = torch.zeros((B, channels, S, S), device=device, dtype=torch.float32)
+        self.time = torch.zeros((B,), device=device, dtype=torch.float32)
+        self.lowres_t = lowres_t.clone() if lowres_t is not None else None
+        self.ex = ex
+        stream = torch.cuda.Stream(device=device)
+        stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(stream):
+            for _ in range(2):  # warm-up: function attributes, allocator pools
+                ex.forward(self.x, self.time, self.lowres_t)
+        torch.cuda.current_stream(device).wait_stream(stream)
+        before = ops.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.pred = ex.forward(self.x, self.time, self.lowres_t)
+        self.launches = ops.launch_count - before
+
+    def __call__(self, img, time_row, lowres_t):
+        self.x.copy_(img)
+        self.time.copy_(time_row)
+        if self.lowres_t is not None:
+            self.lowres_t.copy_(lowres_t)
+        self.graph.replay()
+        ops.launch_count += self.launches
+        return self.pred
+
+
+class Imagen(nn.Module):
+    def __init__(
+        self, unets, *, image_sizes, text_encoder_name=None, text_embed_dim=None, channels=3, timesteps=1000, cond_drop_prob=0.1,
+        loss_type="l2", noise_schedules="cosine", pred_objectives="noise", random_crop_sizes=None, lowres_noise_schedule="linear",
+        lowres_sample_noise_level=0.2, per_sample_random_aug_noise_level=False, condition_on_text=True, auto_normalize_img=True,
+        dynamic_thresholding=True, dynamic_thresholding_percentile=0.95, only_train_unet_number=None, temporal_downsample_factor=1,
+        resize_cond_video_frames=True, resize_mode="nearest", min_snr_loss_weight=True, min_snr_gamma=5, p2_loss_weight_gamma=0.5,
+        p2_loss_weight_k=1,
+    ):
+        super().__init__()
+        self.condition_on_text = condition_on_text
+        self.unconditional = not condition_on_text
+        self.channels = channels
+        unets = cast_tuple(unets)
+        num_unets = len(unets)
+        timesteps = cast_tuple(timesteps, num_unets)
+        noise_schedules = cast_tuple(noise_schedules)
+        noise_schedules = pad_tuple_to_length(noise_schedules, 2, "cosine")
+        noise_schedules = pad_tuple_to_length(noise_schedules, num_unets, "linear")
+        self.noise_schedulers = nn.ModuleList(
+            [NoiseSchedulerSpec(noise_schedule=s, timesteps=t) for t, s in zip(timesteps, noise_schedules)])
+        self.lowres_noise_schedule = NoiseSchedulerSpec(noise_schedule=lowres_noise_schedule)
+        self.pred_objectives = cast_tuple(pred_objectives, num_unets)
+        self.text_embed_dim = default(text_embed_dim, 768)
+        self.unets = nn.ModuleList([])
+        for ind, one_unet in enumerate(unets):
+            assert isinstance(one_unet, (Unet, NullUnet))
+            one_unet = one_unet.cast_model_parameters(
+                lowres_cond=not ind == 0, cond_on_text=self.condition_on_text,
+                text_embed_dim=self.text_embed_dim if self.condition_on_text else None, channels=self.channels, channels_out=self.channels)
+            self.unets.append(one_unet)
+        self.image_sizes = cast_tuple(image_sizes)
+        assert num_unets == len(self.image_sizes), (
+            f"you did not supply the correct number of u-nets ({num_unets}) for resolutions {self.image_sizes}")
+        self.sample_channels = cast_tuple(self.channels, num_unets)
+        lowres_conditions = tuple(u.lowres_cond for u in self.unets)
+        assert lowres_conditions == (False, *((True,) * (num_unets - 1))), (
+            "the first unet must be unconditioned (by low resolution image), and the rest of the unets must have `lowres_cond` set to True")
+        self.random_crop_sizes = cast_tuple(random_crop_sizes, num_unets)
+        self.lowres_sample_noise_level = lowres_sample_noise_level
+        self.cond_drop_prob = cond_drop_prob
+        self.can_classifier_guidance = cond_drop_prob > 0.0
+        self.auto_normalize_img = auto_normalize_img
+        self.dynamic_thresholding = cast_tuple(dynamic_thresholding, num_unets)
+        self.dynamic_thresholding_percentile = dynamic_thresholding_percentile
+        self.register_buffer("_temp", torch.tensor([0.0]), persistent=False)
+        self.use_cuda_graph = True
+        self.noise_fn = None  # tests inject (site, shape, **key) -> tensor; default CounterNoise
+        self.noise_seed = 0
+        self._graphs = {}
+        self.step_hook = None  # optional callable(dict) per inner iteration (parity taps)
+
+    @property
+    def device(self):
+        return self._temp.device
+
+    def normalize_img(self, img):
+        return img * 2 - 1 if self.auto_normalize_img else img
+
+    def _apply(self, fn, *a, **k):
+        self._graphs = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._graphs = {}
+        return super().load_state_dict(*a, **k)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise NotImplementedError("training (Imagen.forward / loss) is outside the sampling hot path built here")
+
+    # ------------------------------------------------------------------ one stage
+    def _unet_step(self, unet, img, time_row, lowres_t, B, S):
+        ex = unet.executor()
+        if not self.use_cuda_graph:
+            return ex.forward(img, time_row, lowres_t)
+        key = (id(ex), B, S, exists(ex.init_base), exists(ex.lowres_img), exists(getattr(ex, 'text', None)))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            g = self._graphs[key] = _StepGraph(ex, B, S, self.channels, lowres_t, img.device)
+        return g(img, time_row, lowres_t)
+
+    def p_sample_loop(self, unet, shape, *, spec, unet_number, noise, lowres_cond_img=None, lowres_noise_level=None,
+                      text_embeds=None, text_mask=None, cond_images=None, inpaint_images=None, inpaint_masks=None,
+                      inpaint_resample_times=5, cond_scale=1.0, pred_objective="noise", dynamic_threshold=True):
+        if cond_scale != 1.0:
+            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is row N4 of the scope table, not built yet")
+        device = self.device
+        B, _, S, _ = shape
+        sched = spec.noise_schedule
+        img = noise("init", shape, device, unet=unet_number).contiguous()
+        has_inpainting = exists(inpaint_images) and exists(inpaint_masks)
+        resample_times = inpaint_resample_times if has_inpainting else 1
+        mask_u8 = None
+        if has_inpainting:
+            inpaint_images = resize_image_to(self.normalize_img(inpaint_images.float()), S).contiguous()
+            mask_u8 = resize_image_to(inpaint_masks[:, None].float(), S).bool()[:, 0].to(torch.uint8).contiguous()
+        ex = unet.executor()
+        ex.set_conditioning(cond_images=cond_images, lowres_cond_img=lowres_cond_img, text_embeds=text_embeds, text_mask=text_mask,
+                            cond_drop_prob=0.0, image_size=S)
+        lowres_t = None
+        if unet.lowres_cond:
+            lt = schedule.log_snr(self.lowres_noise_schedule.noise_schedule, lowres_noise_level)
+            lowres_t = torch.full((B,), float(lt), device=device, dtype=torch.float32)
+        times = schedule.sampling_times(spec.num_timesteps)
+        scal = [schedule.step_scalars(sched, t, tn) for t, tn in times]
+        time_table = torch.tensor([[s["log_snr"]] * B for s in scal], device=device, dtype=torch.float32)
+        ws = torch.empty(ops.lib().kd_dynthresh_workspace_bytes(B), device=device, dtype=torch.uint8)
+        for step, ((t, t_next), sc) in enumerate(zip(times, scal)):
+            is_last_timestep = bool(t_next == 0)
+            for r in reversed(range(resample_times)):
+                if has_inpainting:
+                    ops.inpaint_blend(img, inpaint_images, mask_u8, noise("inpaint", shape, device, unet=unet_number, step=step, r=r),
+                                      sc["alpha"], sc["sigma"])
+                pred = self._unet_step(unet, img, time_table[step], lowres_t, B, S)
+                s = None
+                if dynamic_threshold:
+                    s = ops.dynthresh(img, pred, pred_objective, sc["alpha"], sc["sigma"], self.dynamic_thresholding_percentile, ws)
+                renoise, rn = None, (0.0, 0.0, 1.0)
+                if has_inpainting and not (r == 0 or is_last_timestep):
+                    renoise = noise("renoise", shape, device, unet=unet_number, step=step, r=r)
+                    rn = schedule.renoise_scalars(sched, t_next, t)
+                x_in = img
+                img = ops.ddpm_step(img, pred, noise("p_sample", shape, device, unet=unet_number, step=step, r=r), s, pred_objective,
+                                    sc, renoise=renoise, rn=rn)
+                if exists(self.step_hook):
+                    self.step_hook(dict(unet=unet_number, step=step, r=r, x_in=x_in, pred=pred, img=img))
+        ops.finalize_image(img, inpaint_images if has_inpainting else None, mask_u8)
+        if not self.auto_normalize_img:  # finalize_image un-normalises; undo for the (unused by the reference) raw mode
+            img = img * 2 - 1
+        return img
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def sample(self, texts=None, text_masks=None, text_embeds=None, video_frames=None, cond_images=None, cond_video_frames=None,
+               post_cond_video_frames=None, inpaint_videos=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5,
+               init_images=None, skip_steps=None, batch_size=1, cond_scale=1.0, lowres_sample_noise_level=None,
+               start_at_unet_number=1, start_image_or_video=None, stop_at_unet_number=None, return_all_unet_outputs=False,
+               return_pil_images=False, device=None, use_tqdm=True, use_one_unet_in_gpu=True, noise_key=0):
+        self.eval()
+        device = torch.device(default(device, self.device))
+        if device.type != "cuda":
+            raise RuntimeError("kidney_diffusion_b200.Imagen.sample runs on a B200 only (no CPU fallback); call .cuda() / .to('cuda') first")
+        if next(self.parameters()).device != device:
+            self.to(device)
+        assert not exists(texts), "raw-text encoding (T5) is not part of the reference's sampling path; pass text_embeds"
+        assert not exists(init_images) and not exists(skip_steps), "init_images / skip_steps are unused by the reference"
+        to_dev = lambda t: t.to(device) if exists(t) else None
+        cond_images, text_embeds, text_masks, inpaint_images, inpaint_masks, start_image_or_video = map(
+            to_dev, (cond_images, text_embeds, text_masks, inpaint_images, inpaint_masks, start_image_or_video))
+        if exists(cond_images) and cond_images.dtype == torch.uint8:
+            cond_images = cond_images.float() / 255
+        if not self.unconditional:
+            assert exists(text_embeds), (
+                "text must be passed in if the network was not trained without text `condition_on_text` must be set to `False` when training")
+            text_masks = default(text_masks, lambda: torch.any(text_embeds != 0.0, dim=-1))
+            batch_size = text_embeds.shape[0]
+        inpaint_images = default(inpaint_videos, inpaint_images)
+        if exists(inpaint_images):
+            if self.unconditional and batch_size == 1:
+                batch_size = inpaint_images.shape[0]
+            assert inpaint_images.shape[0] == batch_size, (
+                "number of inpainting images must be equal to the specified batch size on sample `sample(batch_size=<int>)``")
+        assert not (self.condition_on_text and not exists(text_embeds)), "text or text encodings must be passed into imagen if specified"
+        assert not (not self.condition_on_text and exists(text_embeds)), "imagen specified not to be conditioned on text, yet it is presented"
+        assert not (exists(text_embeds) and text_embeds.shape[-1] != self.text_embed_dim), (
+            f"invalid text embedding dimension being passed in (should be {self.text_embed_dim})")
+        assert not (exists(inpaint_images) ^ exists(inpaint_masks)), "inpaint images and masks must be both passed in to do inpainting"
+
+        noise = self.noise_fn
+        if noise is None:
+            noise = CounterNoise(self.noise_seed, noise_key)
+        outputs = []
+        lowres_sample_noise_level = default(lowres_sample_noise_level, self.lowres_sample_noise_level)
+        num_unets = len(self.unets)
+        cond_scale = cast_tuple(cond_scale, num_unets)
+        img = None
+        if start_at_unet_number > 1:
+            assert start_at_unet_number <= num_unets, "must start a unet that is less than the total number of unets"
+            assert not exists(stop_at_unet_number) or start_at_unet_number <= stop_at_unet_number
+            assert exists(start_image_or_video), "starting image or video must be supplied if only doing upscaling"
+            img = resize_image_to(start_image_or_video.float(), self.image_sizes[start_at_unet_number - 2])
+        for unet_number, unet, image_size, spec, pred_objective, dynamic_threshold, unet_cond_scale in zip(
+                range(1, num_unets + 1), self.unets, self.image_sizes, self.noise_schedulers, self.pred_objectives,
+                self.dynamic_thresholding, cond_scale):
+            if unet_number < start_at_unet_number:
+                continue
+            assert not isinstance(unet, NullUnet), "one cannot sample from null / placeholder unets"
+            lowres_cond_img = None
+            if unet.lowres_cond:
+                lowres_cond_img = self.normalize_img(resize_image_to(img, image_size)).contiguous()
+                la, lsig = schedule.alpha_sigma(self.lowres_noise_schedule.noise_schedule, lowres_sample_noise_level)
+                lowres_cond_img = ops.q_sample(lowres_cond_img, noise("lowres_aug", tuple(lowres_cond_img.shape), device, unet=unet_number),
+                                               float(la), float(lsig))
+            shape = (batch_size, self.channels, image_size, image_size)
+            img = self.p_sample_loop(
+                unet, shape, spec=spec, unet_number=unet_number, noise=noise, lowres_cond_img=lowres_cond_img,
+                lowres_noise_level=lowres_sample_noise_level, text_embeds=text_embeds, text_mask=text_masks, cond_images=cond_images,
+                inpaint_images=inpaint_images, inpaint_masks=inpaint_masks, inpaint_resample_times=inpaint_resample_times,
+                cond_scale=unet_cond_scale, pred_objective=pred_objective, dynamic_threshold=dynamic_threshold)
+            outputs.append(img)
+            if exists(stop_at_unet_number) and stop_at_unet_number == unet_number:
+                break
+        out = outputs[-1] if not return_all_unet_outputs else outputs
+        if not return_pil_images:
+            return out
+        from torchvision.transforms import ToPILImage
+
+        pil = [[ToPILImage()(i) for i in o.cpu().unbind(0)] for o in (out if return_all_unet_outputs else [out])]
+        return pil if return_all_unet_outputs else pil[0]

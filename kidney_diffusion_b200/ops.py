@@ -84,15 +84,25 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
     return out
 
 
-def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None):
-    """Plain GEMM y[M,N] = x[M,K] @ w[N,K]^T on tensor cores (mode 2)."""
+def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=None):
+    """Plain GEMM y[M,N] = act(x[M,K] @ w[N,K]^T + bias) + addend on tensor cores (mode 2)."""
     _chk(x, torch.bfloat16, "x")
+    _chk(w, torch.bfloat16, "w")
     M, K = x.shape
     N = w.shape[0]
-    out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    d = KdConvDesc(2, 1, 1, M, K, 0, N, 1, act, 0, 1 if out_f32 else 0, 0 if addend is None or addend.dtype == torch.bfloat16 else 1)
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    else:
+        assert out.is_contiguous() and out.shape == (M, N)
+        out_f32 = out.dtype == torch.float32
+    addend_f32 = 0
+    if addend is not None:
+        assert addend.is_contiguous() and addend.shape == (M, N)
+        addend_f32 = 1 if addend.dtype == torch.float32 else 0
     if bias is not None:
         _chk(bias, torch.float32, "bias")
+    d = KdConvDesc(2, 1, 1, M, K, 0, N, 1, act, 0, 1 if out_f32 else 0, addend_f32)
     check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(x), None, _ptr(w), _ptr(bias), _ptr(addend), None, _ptr(out), _stream()),
           "kd_conv_gemm(mode 2)")
     _count()
@@ -166,11 +176,13 @@ def gn_apply(x, mean_rstd, gamma, beta, *, c_offset, group_size, num_groups, src
     B, H, W, C = x.shape
     y = torch.empty_like(x)
     ctot = ctot if ctot is not None else C
+    ss_stride = 0
     if scale_shift is not None:
-        assert scale_shift.dtype == torch.float32 and scale_shift.stride(-1) == 1 and scale_shift.shape[-1] == 2 * ctot
-        assert scale_shift.is_contiguous()
+        # may be a column slice of the [B, sum(2C)] table produced by one kd_linear_small launch for all blocks
+        assert scale_shift.dtype == torch.float32 and scale_shift.stride(-1) == 1 and scale_shift.shape == (B, 2 * ctot)
+        ss_stride = scale_shift.stride(0)
     check(lib().kd_gn_apply(_ptr(x), _ptr(y), B, H * W, C, c_offset, group_size, num_groups, src_scale, _ptr(mean_rstd),
-                            _ptr(gamma), _ptr(beta), _ptr(scale_shift), ctot, act, _stream()), "kd_gn_apply")
+                            _ptr(gamma), _ptr(beta), _ptr(scale_shift), ss_stride, ctot, act, _stream()), "kd_gn_apply")
     _count()
     return y
 

@@ -1,0 +1,440 @@
+"""CUDA executor of the UNet forward pass (imagen-pytorch 1.18.5 ``Unet.forward`` op order).
+
+Everything that touches activations is a hand-written kernel reached through ``ops`` (C ABI).  torch is used for
+memory, for one-time weight packing, and for the x-independent nearest resize of the conditioning images.
+
+Data layout in HBM: activations NHWC bf16; "raw" tensors (conv outputs / residual stream) and "act" tensors
+(GroupNorm+SiLU applied, the A operand of the next conv) are both bf16; statistics, softmax, time / conditioning towers
+and the GlobalContext gate are fp32.  Weights are packed once: conv [Cout, kh*kw*Cin] bf16 K-major (tap-major,
+channel-minor) so a (tap, 64-channel chunk) k-block is one TMA box.
+
+Fusions relative to the reference's eager graph:
+  * channel concat of the up path is never materialised (two TMA sources in the conv kernel; the 2^-0.5 skip scale is
+    applied inside GroupNorm-apply and folded into res_conv's weight columns),
+  * bias / SiLU / GELU / residual add / GlobalContext gate * h + res_conv(x) / pixel-shuffle run in the conv epilogue,
+  * Downsample's pixel-unshuffle is a 2x2 tap pattern of the TMA loads, Parallel(3x3, 1x1) is one 3x3 conv,
+  * the CrossEmbed init conv is one GEMM (three kernels merged into a 15x15 matrix); its cond-image / low-res part is
+    x-independent and computed once per sample() call,
+  * all ResnetBlock time-MLPs are one launch; to_time_cond + to_lowres_time_cond are one launch.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .modules import Parallel, PixelShuffleUpsample, TransformerBlock, exists
+
+BF16 = torch.bfloat16
+IM2COL_BUDGET_BYTES = 4 << 30
+
+
+def _bf(t):
+    return t.detach().to(BF16).contiguous()
+
+
+def _pack_conv(weight, b_cols=0, b_scale=1.0):
+    """[Cout, Cin, kh, kw] fp32 -> [Cout, kh*kw*Cin] bf16; the last `b_cols` input channels are pre-scaled by b_scale."""
+    w = weight.detach().float()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    if b_cols and b_scale != 1.0:
+        w = w.clone()
+        w[:, w.shape[1] - b_cols:] *= b_scale
+    return _bf(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+
+
+class _Res:
+    """Packed ResnetBlock."""
+
+    def __init__(self, m, b_cols=0, b_scale=1.0):
+        self.dim, self.dim_out, self.G = m.dim, m.dim_out, m.groups
+        self.b_cols, self.b_scale = b_cols, b_scale
+        self.g1, self.be1 = m.block1.groupnorm.weight.detach(), m.block1.groupnorm.bias.detach()
+        self.g2, self.be2 = m.block2.groupnorm.weight.detach(), m.block2.groupnorm.bias.detach()
+        self.w1, self.b1 = _pack_conv(m.block1.project.weight), m.block1.project.bias.detach()
+        self.w2, self.b2 = _pack_conv(m.block2.project.weight), m.block2.project.bias.detach()
+        self.wr = self.br = None
+        if exists(m.res_conv):
+            self.wr, self.br = _pack_conv(m.res_conv.weight, b_cols, b_scale), m.res_conv.bias.detach()
+        self.gca = None
+        if exists(m.gca):
+            C = m.dim_out
+            self.gca = dict(
+                wk=m.gca.to_k.weight.detach().reshape(C).contiguous(), bk=m.gca.to_k.bias.detach(),
+                w0=m.gca.net[0].weight.detach().reshape(-1, C).contiguous(), b0=m.gca.net[0].bias.detach(),
+                w1=m.gca.net[2].weight.detach().reshape(C, -1).contiguous(), b1=m.gca.net[2].bias.detach(),
+            )
+        self.xattn = None
+        if exists(m.cross_attn):
+            a = m.cross_attn.fn
+            self.xattn = dict(
+                heads=a.heads, scale=a.scale, norm_g=a.norm.g.detach().reshape(-1).contiguous(), null_kv=a.null_kv.detach(),
+                wq=_pack_conv(a.to_q.weight), wkv=a.to_kv.weight.detach(), wo=_pack_conv(a.to_out[0].weight),
+                out_g=a.to_out[1].g.detach().reshape(-1).contiguous(),
+            )
+        self.time_w = m.time_mlp[1].weight.detach() if exists(m.time_mlp) else None
+        self.time_b = m.time_mlp[1].bias.detach() if exists(m.time_mlp) else None
+        self.ss_off = None  # column offset into the all-blocks scale/shift table
+
+
+class _Xf:
+    """Packed TransformerBlock."""
+
+    def __init__(self, m):
+        self.layers = []
+        for attn_w, ff in m.layers:
+            a = attn_w.fn
+            d = dict(
+                heads=a.heads, scale=a.scale, norm_g=a.norm.g.detach().reshape(-1).contiguous(), null_kv=a.null_kv.detach(),
+                wqkv=_bf(torch.cat((a.to_q.weight.detach(), a.to_kv.weight.detach()), 0)),
+                wo=_pack_conv(a.to_out[0].weight), out_g=a.to_out[1].g.detach().reshape(-1).contiguous(),
+                ctx=None,
+                ff_g0=ff[0].g.detach().reshape(-1).contiguous(), ff_w1=_pack_conv(ff[1].weight),
+                ff_g1=ff[3].g.detach().reshape(-1).contiguous(), ff_w2=_pack_conv(ff[4].weight),
+            )
+            if exists(a.to_context):
+                d["ctx"] = dict(ln_w=a.to_context[0].weight.detach(), ln_b=a.to_context[0].bias.detach(),
+                                w=a.to_context[1].weight.detach(), b=a.to_context[1].bias.detach())
+            self.layers.append(d)
+
+
+class UnetExecutor:
+    def __init__(self, unet, device, stamp):
+        ops.lib()  # fail loudly if the CUDA library or a B200 is missing
+        self.stamp, self.device, self.u = stamp, device, unet
+        u = unet
+        self.skip_scale = u.skip_connect_scale
+        self.dim = u.init_conv.convs[0].out_channels + u.init_conv.convs[1].out_channels + u.init_conv.convs[2].out_channels
+        # ---- init conv: merge the CrossEmbed kernels into one KxK matrix (K = largest kernel)
+        ks = max(u.init_conv.kernel_sizes)
+        self.init_ks = ks
+        Cin = u.init_channels
+        Wm = torch.zeros(self.dim, ks, ks, Cin, device=device)
+        bias = torch.zeros(self.dim, device=device)
+        o = 0
+        for conv in u.init_conv.convs:
+            k, co = conv.kernel_size[0], conv.out_channels
+            off = (ks - k) // 2
+            Wm[o:o + co, off:off + k, off:off + k, :] = conv.weight.detach().permute(0, 2, 3, 1)
+            bias[o:o + co] = conv.bias.detach()
+            o += co
+        Cc = u.cond_images_channels
+        x_idx = list(range(Cc, Cc + u.channels))
+        fixed_idx = [i for i in range(Cin) if i not in x_idx]  # [cond..., lowres...]
+        self.init_bias = bias
+
+        def pack_panel_w(idx):
+            K = ks * ks * len(idx)
+            Kp = ((K + 63) // 64) * 64
+            W = torch.zeros(self.dim, Kp, device=device)
+            W[:, :K] = Wm[..., idx].reshape(self.dim, K)
+            return _bf(W), Kp
+
+        self.init_wx, self.init_kpx = pack_panel_w(x_idx)
+        self.n_fixed = len(fixed_idx)
+        if self.n_fixed:
+            self.init_wf, self.init_kpf = pack_panel_w(fixed_idx)
+
+        # ---- conditioning towers
+        self.Tc, self.cd = u.time_cond_dim, u.cond_dim
+        self.sinu_w = u.to_time_hiddens[0].weights.detach()
+        self.th_w, self.th_b = u.to_time_hiddens[1].weight.detach(), u.to_time_hiddens[1].bias.detach()
+        self.tok_w, self.tok_b = u.to_time_tokens[0].weight.detach(), u.to_time_tokens[0].bias.detach()
+        tc_w, tc_b = [u.to_time_cond[0].weight.detach()], u.to_time_cond[0].bias.detach().clone()
+        self.lowres = u.lowres_cond
+        if self.lowres:
+            self.lsinu_w = u.to_lowres_time_hiddens[0].weights.detach()
+            self.lth_w, self.lth_b = u.to_lowres_time_hiddens[1].weight.detach(), u.to_lowres_time_hiddens[1].bias.detach()
+            self.ltok_w, self.ltok_b = u.to_lowres_time_tokens[0].weight.detach(), u.to_lowres_time_tokens[0].bias.detach()
+            tc_w.append(u.to_lowres_time_cond[0].weight.detach())
+            tc_b += u.to_lowres_time_cond[0].bias.detach()
+        self.tc_w, self.tc_b = torch.cat(tc_w, 1).contiguous(), tc_b.contiguous()  # t = [th | lowres_th] @ [Wc | Wlc]^T + (bc + blc)
+        self.n_time_tokens = u.num_time_tokens * (2 if self.lowres else 1)
+        self.nc_w, self.nc_b = u.norm_cond.weight.detach(), u.norm_cond.bias.detach()
+
+        # ---- body
+        s = self.skip_scale
+        self.blocks = []  # every packed ResnetBlock, for the batched time-MLP
+
+        def res(m, b_cols=0, b_scale=1.0):
+            r = _Res(m, b_cols, b_scale)
+            self.blocks.append(r)
+            return r
+
+        self.init_res = res(u.init_resnet_block) if exists(u.init_resnet_block) else None
+        self.downs = []
+        for pre, init_block, blocks, attn, post in u.downs:
+            d = dict(pre=None, post=None, post_parallel=None)
+            if exists(pre):
+                d["pre"] = self._pack_down(pre[1])
+            d["init"] = res(init_block)
+            d["blocks"] = [res(b) for b in blocks]
+            d["attn"] = _Xf(attn) if isinstance(attn, TransformerBlock) else None
+            if exists(post):
+                if isinstance(post, Parallel):
+                    c3, c1 = post.fns
+                    w = c3.weight.detach().clone()
+                    w[:, :, 1, 1] += c1.weight.detach()[:, :, 0, 0]
+                    d["post_parallel"] = (_pack_conv(w), (c3.bias.detach() + c1.bias.detach()).contiguous())
+                else:
+                    d["post"] = self._pack_down(post[1])
+            self.downs.append(d)
+        self.mid1 = res(u.mid_block1)
+        self.mid_attn = _Xf(u.mid_attn) if exists(u.mid_attn) else None
+        self.mid2 = res(u.mid_block2)
+        self.ups = []
+        for init_block, blocks, attn, up in u.ups:
+            skip_c = init_block.dim - init_block.dim_out
+            d = dict(init=res(init_block, skip_c, s), blocks=[res(b, b.dim - b.dim_out, s) for b in blocks],
+                     attn=_Xf(attn) if isinstance(attn, TransformerBlock) else None, up=None)
+            if isinstance(up, PixelShuffleUpsample):
+                conv = up.net[0]
+                co4, ci = conv.weight.shape[0], conv.weight.shape[1]
+                co = co4 // 4
+                w = conv.weight.detach().view(co, 4, ci).permute(1, 0, 2).reshape(co4, ci)  # rows (dy*2+dx, c)
+                b = conv.bias.detach().view(co, 4).t().reshape(-1).contiguous()
+                d["up"] = (_bf(w), b)
+            self.ups.append(d)
+        self.final_res = res(u.final_res_block, 0, 1.0)
+        self.final_w = u.final_conv.weight.detach().permute(0, 2, 3, 1).contiguous()  # [Cout,3,3,Cin] fp32
+        self.final_b = u.final_conv.bias.detach()
+
+        # ---- all time-MLPs as one matrix
+        off = 0
+        ws, bs = [], []
+        for r in self.blocks:
+            if r.time_w is not None:
+                r.ss_off = off
+                off += r.time_w.shape[0]
+                ws.append(r.time_w)
+                bs.append(r.time_b)
+        self.ss_w, self.ss_b = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
+
+        # ---- per-sample conditioning state
+        self.cond_key = None
+        self.init_base = None
+        self.lowres_img = None
+        self._static = {}
+        if u.cond_on_text:
+            self._pack_text()
+
+    # ------------------------------------------------------------------ packing helpers
+    @staticmethod
+    def _pack_down(conv):
+        co, c4 = conv.weight.shape[0], conv.weight.shape[1]
+        c = c4 // 4
+        w = conv.weight.detach().view(co, c, 2, 2)  # input channel = c*4 + dy*2 + dx
+        return _bf(w.permute(0, 2, 3, 1).reshape(co, 4 * c)), conv.bias.detach()
+
+    def _pack_text(self):
+        self.text_ready = False  # built lazily by text.py
+
+    # ------------------------------------------------------------------ x-independent conditioning (once per sample() call)
+    def set_conditioning(self, *, cond_images, lowres_cond_img, text_embeds, text_mask, cond_drop_prob, image_size):
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if exists(t) else None
+                    for t in (cond_images, lowres_cond_img, text_embeds, text_mask)) + (cond_drop_prob, image_size)
+        if key == self.cond_key:
+            return
+        self.cond_key = key
+        self.text = None
+        if exists(text_embeds) and self.u.cond_on_text:
+            from .text import text_conditioning
+
+            self.text = text_conditioning(self, text_embeds, text_mask, cond_drop_prob)
+        # static per-(B, S) buffers: captured CUDA graphs keep pointing at valid, refreshed conditioning
+        B = (lowres_cond_img if exists(lowres_cond_img) else cond_images).shape[0] if (exists(lowres_cond_img) or exists(cond_images)) else 0
+        st = self._static.setdefault((B, image_size), {})
+        self.lowres_img = None
+        if exists(lowres_cond_img):
+            if "lowres" not in st:
+                st["lowres"] = torch.empty_like(lowres_cond_img, dtype=torch.float32).contiguous()
+            st["lowres"].copy_(lowres_cond_img)
+            self.lowres_img = st["lowres"]
+        self.init_base = None
+        if self.n_fixed:
+            parts = []
+            if exists(cond_images):
+                ci = cond_images.float()
+                if ci.shape[-1] != image_size:
+                    ci = F.interpolate(ci, image_size, mode="nearest")  # resize_image_to(..., mode='nearest'), x-independent
+                parts.append(ci)
+            if exists(lowres_cond_img):
+                parts.append(self.lowres_img)
+            fixed = torch.cat(parts, 1).contiguous()
+            assert fixed.shape[1] == self.n_fixed
+            S = fixed.shape[-1]
+            if "init_base" not in st:
+                st["init_base"] = torch.empty((B, S, S, self.dim), device=fixed.device, dtype=BF16)
+            self.init_base = st["init_base"]
+            self._init_gemm(fixed, self.init_wf, self.init_kpf, None, None, self.init_base)
+
+    def _init_gemm(self, img, w, Kp, bias, addend, out):
+        B, _, S, S2 = img.shape
+        per = S * S2 * Kp * 2
+        chunk = max(1, min(B, IM2COL_BUDGET_BYTES // per))
+        for b0 in range(0, B, chunk):
+            b1 = min(B, b0 + chunk)
+            panel = ops.im2col_nchw(img[b0:b1], self.init_ks, Kp)
+            ops.gemm_rows(panel, w, bias, addend=None if addend is None else addend[b0:b1].view(-1, self.dim),
+                          out=out[b0:b1].view(-1, self.dim))
+            del panel
+
+    # ------------------------------------------------------------------ blocks
+    def _gn(self, xa, xb, b_scale, G, gamma, beta, ss):
+        """GroupNorm(+scale/shift)+SiLU over the (virtual) concat [xa | b_scale * xb] -> activated (ya, yb)."""
+        B, H, W, Ca = xa.shape
+        Cb = xb.shape[3] if exists(xb) else 0
+        C = Ca + Cb
+        gs = C // G
+        pa = ops.gn_stats(xa, 0, gs, G)
+        pb = ops.gn_stats(xb, Ca, gs, G) if exists(xb) else None
+        mr = ops.gn_finalize(pa, 1.0, pb, b_scale, count=gs * H * W)
+        kw = dict(group_size=gs, num_groups=G, scale_shift=ss, ctot=C)
+        ya = ops.gn_apply(xa, mr, gamma, beta, c_offset=0, **kw)
+        yb = ops.gn_apply(xb, mr, gamma, beta, c_offset=Ca, src_scale=b_scale, **kw) if exists(xb) else None
+        return ya, yb
+
+    def _cross_attn(self, P, h, c):
+        B, H, W, C = h.shape
+        J = c.shape[1]
+        xn = ops.layernorm_bf16(h, P["norm_g"])
+        q = ops.conv_gemm(xn, P["wq"], None, ksize=1)
+        kv = ops.linear_small(c.view(B * J, -1), P["wkv"]).view(B, J, -1)
+        o = ops.attn_cross(q.view(B, H * W, -1), kv, P["null_kv"], P["heads"], P["scale"])
+        o = ops.conv_gemm(o.view(B, H, W, -1), P["wo"], None, ksize=1)
+        return ops.layernorm_bf16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
+
+    def _resnet(self, P, xa, xb, ss_all, c):
+        B = xa.shape[0]
+        a1, a1b = self._gn(xa, xb, P.b_scale, P.G, P.g1, P.be1, None)
+        h = ops.conv_gemm(a1, P.w1, P.b1, xb=a1b, ksize=3)
+        if exists(P.xattn):
+            h = self._cross_attn(P.xattn, h, c)
+        ss = ss_all[:, P.ss_off:P.ss_off + 2 * P.dim_out] if P.ss_off is not None else None
+        a2, _ = self._gn(h, None, 1.0, P.G, P.g2, P.be2, ss)
+        if exists(P.gca):
+            g = P.gca
+            h2 = ops.conv_gemm(a2, P.w2, P.b2, ksize=3)
+            logits = ops.rowdot(h2, g["wk"], g["bk"])
+            pooled = ops.gca_pool(h2, logits)
+            hid = ops.linear_small(pooled, g["w0"], g["b0"], post_act=ops.ACT_SILU)
+            gate = ops.linear_small(hid, g["w1"], g["b1"], post_act=ops.ACT_SIGMOID)
+            if exists(P.wr):  # out = res_conv(x) + gate * h2, fused in the 1x1 conv epilogue
+                return ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1, addend=h2, addend_scale=gate)
+            return ops.gate_residual(h2, gate, xa)
+        if exists(P.wr):
+            r = ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1)
+            return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=r)
+        return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=xa)
+
+    def _transformer(self, P, x, c):
+        B, H, W, C = x.shape
+        N = H * W
+        for L in P.layers:
+            xn = ops.layernorm_bf16(x, L["norm_g"])
+            qkv = ops.conv_gemm(xn, L["wqkv"], None, ksize=1).view(B, N, -1)
+            ctx_kv = None
+            if exists(c) and exists(L["ctx"]):
+                J = c.shape[1]
+                cn = ops.layernorm_f32(c.view(B * J, -1), L["ctx"]["ln_w"], L["ctx"]["ln_b"])
+                ctx_kv = ops.linear_small(cn, L["ctx"]["w"], L["ctx"]["b"]).view(B, J, -1)
+            kv = ops.kv_assemble(qkv, L["heads"] * 64, ctx_kv, L["null_kv"])
+            o = ops.attn_mqa(qkv, kv, L["heads"], L["scale"])
+            o = ops.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
+            x = ops.layernorm_bf16(o, L["out_g"], residual=x)
+            f = ops.layernorm_bf16(x, L["ff_g0"])
+            f = ops.conv_gemm(f, L["ff_w1"], None, ksize=1, act=ops.ACT_GELU)
+            f = ops.layernorm_bf16(f, L["ff_g1"])
+            x = ops.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
+        return x
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, time, lowres_noise_times=None, taps=None):
+        u = self.u
+        x = x.contiguous().float()
+        B, _, S, S2 = x.shape
+        dev = x.device
+        Tc, cd = self.Tc, self.cd
+        # --- conditioning towers (x-independent, tiny)
+        nT = 2 if self.lowres else 1
+        hid = torch.empty((B, nT * Tc), device=dev, dtype=torch.float32)
+        J_time = self.n_time_tokens
+        text = getattr(self, "text", None)
+        J = J_time + (text["tokens"].shape[1] if exists(text) else 0)
+        c_raw = torch.empty((B, J, cd), device=dev, dtype=torch.float32)
+        c_flat = c_raw.view(B, J * cd)
+        ops.linear_small(ops.sinu_emb(time.float().contiguous(), self.sinu_w), self.th_w, self.th_b, post_act=ops.ACT_SILU,
+                         out=hid[:, :Tc], ldy=nT * Tc)
+        ops.linear_small(hid[:, :Tc], self.tok_w, self.tok_b, out=c_flat[:, : u.num_time_tokens * cd], ldy=J * cd)
+        if self.lowres:
+            ops.linear_small(ops.sinu_emb(lowres_noise_times.float().contiguous(), self.lsinu_w), self.lth_w, self.lth_b,
+                             post_act=ops.ACT_SILU, out=hid[:, Tc:], ldy=nT * Tc)
+            ops.linear_small(hid[:, Tc:], self.ltok_w, self.ltok_b,
+                             out=c_flat[:, u.num_time_tokens * cd: 2 * u.num_time_tokens * cd], ldy=J * cd)
+        if exists(text):
+            c_raw[:, J_time:] = text["tokens"]  # x- and t-independent, prepared once per sample() call
+            t = ops.linear_small(torch.cat((hid, text["hidden_in"]), 1), text["tc_w"], text["tc_b"])
+        else:
+            t = ops.linear_small(hid, self.tc_w, self.tc_b)
+        c = ops.layernorm_f32(c_raw, self.nc_w, self.nc_b)
+        ss_all = ops.linear_small(t, self.ss_w, self.ss_b, pre_act=ops.ACT_SILU)
+        if taps is not None:
+            taps["t"], taps["c"] = t, c
+
+        # --- init conv (per-step part: the 3 image channels of x; fixed part added in the epilogue)
+        h = torch.empty((B, S, S2, self.dim), device=dev, dtype=BF16)
+        self._init_gemm(x, self.init_wx, self.init_kpx, self.init_bias, self.init_base, h)
+        if taps is not None:
+            taps["init_conv"] = h
+        init_residual = h if u.init_conv_to_final_conv_residual else None
+        if exists(self.init_res):
+            h = self._resnet(self.init_res, h, None, ss_all, None)
+            if taps is not None:
+                taps["init_resnet_block"] = h
+
+        hiddens = []
+        for li, d in enumerate(self.downs):
+            if exists(d["pre"]):
+                h = ops.conv_gemm(h, d["pre"][0], d["pre"][1], mode=1)
+            h = self._resnet(d["init"], h, None, ss_all, c)
+            for P in d["blocks"]:
+                h = self._resnet(P, h, None, ss_all, None)
+                hiddens.append(h)
+            if exists(d["attn"]):
+                h = self._transformer(d["attn"], h, c)
+            hiddens.append(h)
+            if exists(d["post"]):
+                h = ops.conv_gemm(h, d["post"][0], d["post"][1], mode=1)
+            elif exists(d["post_parallel"]):
+                h = ops.conv_gemm(h, d["post_parallel"][0], d["post_parallel"][1], ksize=3)
+            if taps is not None:
+                taps[f"down{li}"] = h
+
+        h = self._resnet(self.mid1, h, None, ss_all, c)
+        if taps is not None:
+            taps["mid_block1"] = h
+        if exists(self.mid_attn):
+            h = self._transformer(self.mid_attn, h, None)
+            if taps is not None:
+                taps["mid_attn"] = h
+        h = self._resnet(self.mid2, h, None, ss_all, c)
+        if taps is not None:
+            taps["mid_block2"] = h
+
+        for li, d in enumerate(self.ups):
+            h = self._resnet(d["init"], h, hiddens.pop(), ss_all, c)
+            for P in d["blocks"]:
+                h = self._resnet(P, h, hiddens.pop(), ss_all, None)
+            if exists(d["attn"]):
+                h = self._transformer(d["attn"], h, c)
+            if exists(d["up"]):
+                h = ops.conv_gemm(h, d["up"][0], d["up"][1], ksize=1, act=ops.ACT_SILU, out_mode=1)
+            if taps is not None:
+                taps[f"up{li}"] = h
+
+        h = self._resnet(self.final_res, h, init_residual, ss_all, None)
+        if taps is not None:
+            taps["final_res_block"] = h
+        return ops.final_conv(h, self.lowres_img, self.final_w, self.final_b)

@@ -1,0 +1,141 @@
+"""UNet forward + sampler parity: CUDA path (through the C ABI) vs the fp32 CPU oracle on identical random-init weights and
+identical injected noise.  Tolerance from BASELINE.json north_star: rel-L2 <= 1e-2 per step UNet output (bf16 path) and
+on final samples."""
+import pytest
+import torch
+
+from helpers import U1_KW, U2_KW, U3_KW, KeyedNoise, make_pair, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _report(taps_dev, taps_ref):
+    for k, v in taps_ref.items():
+        if k in taps_dev and torch.is_tensor(v) and v.dim() == 4:
+            d = taps_dev[k].float().cpu().permute(0, 3, 1, 2)
+            print(f"   tap {k:18s} rel_l2={rel_l2(d, v):.3e}")
+        elif k in taps_dev and torch.is_tensor(v):
+            print(f"   tap {k:18s} rel_l2={rel_l2(taps_dev[k], v):.3e}")
+
+
+@pytest.mark.parametrize("name,kw,lowres,S,B", [
+    ("u3", U3_KW, True, 128, 2),
+    ("u2", U2_KW, True, 64, 2),
+    ("u1", U1_KW, False, 32, 3),
+    ("u3_b1_rect", U3_KW, True, 64, 1),
+])
+def test_unet_forward_parity(cuda_lib, name, kw, lowres, S, B):
+    ou, pu = make_pair(kw, lowres_cond=lowres, seed=hash(name) % 1000)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, S, S, generator=g)
+    t = torch.tensor([2.18, -0.5, 5.0])[:B]
+    lr = torch.randn(B, 3, S, S, generator=g) if lowres else None
+    lt = torch.full((B,), 0.7093) if lowres else None
+    cond = torch.rand(B, kw.get("cond_images_channels", 0), S * 2, S * 2, generator=g) if kw.get("cond_images_channels") else None
+    taps_ref = {}
+    with torch.no_grad():
+        ref = ou(x, t, lowres_cond_img=lr, lowres_noise_times=lt, cond_images=cond, taps=taps_ref)
+    dev = lambda v: None if v is None else v.cuda()
+    ex = pu.executor()
+    ex.set_conditioning(cond_images=dev(cond), lowres_cond_img=dev(lr), text_embeds=None, text_mask=None, cond_drop_prob=0.0, image_size=S)
+    taps_dev = {}
+    out = ex.forward(dev(x), dev(t), dev(lt), taps=taps_dev)
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    print(f"[{name}] unet output rel_l2 = {err:.3e}")
+    _report(taps_dev, taps_ref)
+    # public forward() gives the same result
+    out2 = pu(dev(x), dev(t), lowres_cond_img=dev(lr), lowres_noise_times=dev(lt), cond_images=dev(cond))
+    assert torch.equal(out, out2)
+    assert err < TOL
+
+
+def _imagen_pair(kws, image_sizes, timesteps, objectives):
+    from kidney_diffusion_b200 import Imagen, NullUnet, Unet
+    from oracle import imagen_oracle as O
+
+    torch.manual_seed(11)
+    ounets, punets = [], []
+    for i, kw in enumerate(kws):
+        if kw is None:
+            on, pn = O.NullUnet(), NullUnet()
+            on.lowres_cond = pn.lowres_cond = i > 0
+            ounets.append(on); punets.append(pn)
+        else:
+            ounets.append(O.Unet(**kw)); punets.append(Unet(**kw))
+    oi = O.Imagen(unets=tuple(ounets), image_sizes=image_sizes, timesteps=timesteps, pred_objectives=objectives, condition_on_text=False)
+    O.randomize_zero_init_(oi)
+    pi = Imagen(unets=tuple(punets), image_sizes=image_sizes, timesteps=timesteps, pred_objectives=objectives,
+                random_crop_sizes=(None,) * len(kws), condition_on_text=False)
+    pi.load_state_dict(oi.state_dict())
+    return oi.eval(), pi.cuda().eval()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sample_parity_sr_stage_with_inpainting(cuda_lib, use_graph):
+    """Config-3/4 shaped stage (SR unet, v objective, cond image, low-res conditioning, RePaint inpainting r=2)."""
+    oi, pi = _imagen_pair([None, U3_KW], (32, 128), (4, 5), ("noise", "v"))
+    pi.use_cuda_graph = use_graph
+    kn = KeyedNoise(99)
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    cond = torch.rand(B, 3, 256, 256, generator=g)
+    start = torch.rand(B, 3, 32, 32, generator=g)
+    inp = torch.rand(B, 3, 128, 128, generator=g)
+    mask = torch.zeros(B, 128, 128)
+    mask[:, :32, :] = 1
+    mask[:, :, :32] = 1
+    ref_steps = []
+    ref = oi.sample(batch_size=B, cond_images=cond, start_image_or_video=start, start_at_unet_number=2, stop_at_unet_number=2,
+                    inpaint_images=inp, inpaint_masks=mask, inpaint_resample_times=2, noise_fn=kn.cpu, step_taps=ref_steps)
+    dev_steps = []
+    pi.noise_fn = kn.dev
+    pi.step_hook = lambda d: dev_steps.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()})
+    out = pi.sample(batch_size=B, cond_images=cond, start_image_or_video=start, start_at_unet_number=2, stop_at_unet_number=2,
+                    inpaint_images=inp, inpaint_masks=mask, inpaint_resample_times=2, use_tqdm=False, device="cuda")
+    torch.cuda.synchronize()
+    assert len(dev_steps) == len(ref_steps) == 10
+    worst = 0.0
+    for i, (d, r) in enumerate(zip(dev_steps, ref_steps)):
+        e_in, e_pred, e_img = rel_l2(d["x_in"], r["x_in"]), rel_l2(d["pred"], r["pred"]), rel_l2(d["img"], r["img"])
+        print(f"  step {i}: x_in {e_in:.2e} pred {e_pred:.2e} img {e_img:.2e}")
+        worst = max(worst, e_pred)
+    err = rel_l2(out, ref)
+    print(f"final sample rel_l2 = {err:.3e}; worst per-step pred = {worst:.3e}")
+    assert out.shape == (B, 3, 128, 128) and float(out.min()) >= 0 and float(out.max()) <= 1
+    # inpainted region equals the supplied pixels up to the normalise / un-normalise round trip
+    m = mask.bool()[:, None].expand_as(inp)
+    assert float((out.cpu()[m] - inp[m]).abs().max()) < 1e-6
+    assert worst < TOL and err < TOL
+
+
+def test_sample_parity_base_stage(cuda_lib):
+    """Config-1 shaped run: unconditional base unet, eps objective, 6 steps, batch 4."""
+    oi, pi = _imagen_pair([U1_KW], (32,), (6,), ("noise",))
+    kn = KeyedNoise(7)
+    ref_steps, dev_steps = [], []
+    ref = oi.sample(batch_size=4, noise_fn=kn.cpu, step_taps=ref_steps)
+    pi.noise_fn = kn.dev
+    pi.step_hook = lambda d: dev_steps.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()})
+    out = pi.sample(batch_size=4, use_tqdm=False, device="cuda")
+    worst = max(rel_l2(d["pred"], r["pred"]) for d, r in zip(dev_steps, ref_steps))
+    err = rel_l2(out, ref)
+    print(f"base stage: final rel_l2 = {err:.3e}, worst per-step pred = {worst:.3e}")
+    assert worst < TOL and err < TOL
+
+
+def test_counter_noise_is_deterministic_and_keyed(cuda_lib):
+    _, pi = _imagen_pair([U1_KW], (32,), (2,), ("noise",))
+    a = pi.sample(batch_size=2, use_tqdm=False, device="cuda", noise_key=5)
+    b = pi.sample(batch_size=2, use_tqdm=False, device="cuda", noise_key=5)
+    c = pi.sample(batch_size=2, use_tqdm=False, device="cuda", noise_key=6)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_no_cpu_fallback(cuda_lib):
+    from kidney_diffusion_b200 import Unet
+
+    u = Unet(**U1_KW, cond_on_text=False, text_embed_dim=None)
+    with pytest.raises(RuntimeError):
+        u(torch.randn(1, 3, 32, 32), torch.zeros(1))
