@@ -129,7 +129,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
 __global__ void rowdot_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                               float* __restrict__ out, long rows, int C) {
   const int oct = C >> 3;
-  const int sub = oct < 32 ? oct : 32;  // lanes cooperating on one pixel (power of two)
+  const int sub = (oct < 32 && (oct & (oct - 1)) == 0) ? oct : 32;  // lanes cooperating on one pixel (power of two)
   const int ppw = 32 / sub;             // pixels per warp
   const int lane = threadIdx.x & 31;
   const long warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -392,9 +392,8 @@ extern "C" int kd_rowdot(const void* x, const float* w, const float* bias, float
   KD_REQUIRE(x && w && out && B > 0 && HW > 0, "kd_rowdot: bad argument");
   KD_CHECK_OCT(C);
   const int oct = C / 8;
-  KD_REQUIRE(oct >= 32 || (oct & (oct - 1)) == 0, "kd_rowdot: C/8 = %d must be a power of two when < 32", oct);
   const long rows = (long)B * HW;
-  const int sub = oct < 32 ? oct : 32;
+  const int sub = (oct < 32 && (oct & (oct - 1)) == 0) ? oct : 32;
   long blocks = (rows / (32 / sub) + 7) / 8;  // 8 warps per block
   const long cap = (long)kd_num_sms() * 16;
   if (blocks > cap) blocks = cap;

@@ -84,6 +84,71 @@ class _StepGraph:
         return self.pred
 
 
+class StageRun:
+    """One stage of the cascade: p_sample_loop state resident in HBM.  ``step(k, r)`` is one *patch-step* (the unit of the
+    headline metric): [RePaint blend] -> UNet forward -> exact dynamic threshold -> fused p_sample update [+ re-noise]."""
+
+    def __init__(self, imagen, unet_number, shape, *, noise, lowres_cond_img, lowres_noise_level, text_embeds, text_mask, cond_images,
+                 inpaint_images, inpaint_masks, inpaint_resample_times, cond_scale):
+        if cond_scale != 1.0:
+            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is row N4 of the scope table, not built yet")
+        self.im, self.unet_number, self.shape, self.noise = imagen, unet_number, tuple(shape), noise
+        self.unet = unet = imagen.unets[unet_number - 1]
+        spec = imagen.noise_schedulers[unet_number - 1]
+        self.sched = spec.noise_schedule
+        self.objective = imagen.pred_objectives[unet_number - 1]
+        self.dynamic_threshold = imagen.dynamic_thresholding[unet_number - 1]
+        self.device = device = imagen.device
+        B, _, S, _ = shape
+        self.B, self.S = B, S
+        self.img = noise("init", self.shape, device, unet=unet_number).contiguous()
+        self.has_inpainting = exists(inpaint_images) and exists(inpaint_masks)
+        self.resample_times = inpaint_resample_times if self.has_inpainting else 1
+        self.inpaint, self.mask_u8 = None, None
+        if self.has_inpainting:
+            self.inpaint = resize_image_to(imagen.normalize_img(inpaint_images.float()), S).contiguous()
+            self.mask_u8 = resize_image_to(inpaint_masks[:, None].float(), S).bool()[:, 0].to(torch.uint8).contiguous()
+        self.ex = unet.executor()
+        self.ex.set_conditioning(cond_images=cond_images, lowres_cond_img=lowres_cond_img, text_embeds=text_embeds, text_mask=text_mask,
+                                 cond_drop_prob=0.0, image_size=S)
+        self.lowres_t = None
+        if unet.lowres_cond:
+            lt = schedule.log_snr(imagen.lowres_noise_schedule.noise_schedule, lowres_noise_level)
+            self.lowres_t = torch.full((B,), float(lt), device=device, dtype=torch.float32)
+        self.times = schedule.sampling_times(spec.num_timesteps)
+        self.num_steps = len(self.times)
+        self.scal = [schedule.step_scalars(self.sched, t, tn) for t, tn in self.times]
+        self.time_table = torch.tensor([[s["log_snr"]] * B for s in self.scal], device=device, dtype=torch.float32)
+        self.ws = torch.empty(ops.lib().kd_dynthresh_workspace_bytes(B), device=device, dtype=torch.uint8)
+
+    def step(self, step, r=0):
+        im, sc, n = self.im, self.scal[step], self.unet_number
+        t, t_next = self.times[step]
+        if self.has_inpainting:
+            ops.inpaint_blend(self.img, self.inpaint, self.mask_u8, self.noise("inpaint", self.shape, self.device, unet=n, step=step, r=r),
+                              sc["alpha"], sc["sigma"])
+        pred = im._unet_step(self.unet, self.img, self.time_table[step], self.lowres_t, self.B, self.S)
+        s = None
+        if self.dynamic_threshold:
+            s = ops.dynthresh(self.img, pred, self.objective, sc["alpha"], sc["sigma"], im.dynamic_thresholding_percentile, self.ws)
+        renoise, rn = None, (0.0, 0.0, 1.0)
+        if self.has_inpainting and not (r == 0 or bool(t_next == 0)):
+            renoise = self.noise("renoise", self.shape, self.device, unet=n, step=step, r=r)
+            rn = schedule.renoise_scalars(self.sched, t_next, t)
+        x_in = self.img
+        self.img = ops.ddpm_step(x_in, pred, self.noise("p_sample", self.shape, self.device, unet=n, step=step, r=r), s, self.objective, sc,
+                                 renoise=renoise, rn=rn)
+        if exists(im.step_hook):
+            im.step_hook(dict(unet=n, step=step, r=r, x_in=x_in, pred=pred, img=self.img))
+        return self.img
+
+    def finish(self):
+        img = ops.finalize_image(self.img, self.inpaint if self.has_inpainting else None, self.mask_u8)
+        if not self.im.auto_normalize_img:  # finalize_image un-normalises; undo for the (unused by the reference) raw mode
+            img = img * 2 - 1
+        return img
+
+
 class Imagen(nn.Module):
     def __init__(
         self, unets, *, image_sizes, text_encoder_name=None, text_embed_dim=None, channels=3, timesteps=1000, cond_drop_prob=0.1,
@@ -167,55 +232,19 @@ class Imagen(nn.Module):
             g = self._graphs[key] = _StepGraph(ex, B, S, self.channels, lowres_t, img.device)
         return g(img, time_row, lowres_t)
 
-    def p_sample_loop(self, unet, shape, *, spec, unet_number, noise, lowres_cond_img=None, lowres_noise_level=None,
-                      text_embeds=None, text_mask=None, cond_images=None, inpaint_images=None, inpaint_masks=None,
-                      inpaint_resample_times=5, cond_scale=1.0, pred_objective="noise", dynamic_threshold=True):
-        if cond_scale != 1.0:
-            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is row N4 of the scope table, not built yet")
-        device = self.device
-        B, _, S, _ = shape
-        sched = spec.noise_schedule
-        img = noise("init", shape, device, unet=unet_number).contiguous()
-        has_inpainting = exists(inpaint_images) and exists(inpaint_masks)
-        resample_times = inpaint_resample_times if has_inpainting else 1
-        mask_u8 = None
-        if has_inpainting:
-            inpaint_images = resize_image_to(self.normalize_img(inpaint_images.float()), S).contiguous()
-            mask_u8 = resize_image_to(inpaint_masks[:, None].float(), S).bool()[:, 0].to(torch.uint8).contiguous()
-        ex = unet.executor()
-        ex.set_conditioning(cond_images=cond_images, lowres_cond_img=lowres_cond_img, text_embeds=text_embeds, text_mask=text_mask,
-                            cond_drop_prob=0.0, image_size=S)
-        lowres_t = None
-        if unet.lowres_cond:
-            lt = schedule.log_snr(self.lowres_noise_schedule.noise_schedule, lowres_noise_level)
-            lowres_t = torch.full((B,), float(lt), device=device, dtype=torch.float32)
-        times = schedule.sampling_times(spec.num_timesteps)
-        scal = [schedule.step_scalars(sched, t, tn) for t, tn in times]
-        time_table = torch.tensor([[s["log_snr"]] * B for s in scal], device=device, dtype=torch.float32)
-        ws = torch.empty(ops.lib().kd_dynthresh_workspace_bytes(B), device=device, dtype=torch.uint8)
-        for step, ((t, t_next), sc) in enumerate(zip(times, scal)):
-            is_last_timestep = bool(t_next == 0)
-            for r in reversed(range(resample_times)):
-                if has_inpainting:
-                    ops.inpaint_blend(img, inpaint_images, mask_u8, noise("inpaint", shape, device, unet=unet_number, step=step, r=r),
-                                      sc["alpha"], sc["sigma"])
-                pred = self._unet_step(unet, img, time_table[step], lowres_t, B, S)
-                s = None
-                if dynamic_threshold:
-                    s = ops.dynthresh(img, pred, pred_objective, sc["alpha"], sc["sigma"], self.dynamic_thresholding_percentile, ws)
-                renoise, rn = None, (0.0, 0.0, 1.0)
-                if has_inpainting and not (r == 0 or is_last_timestep):
-                    renoise = noise("renoise", shape, device, unet=unet_number, step=step, r=r)
-                    rn = schedule.renoise_scalars(sched, t_next, t)
-                x_in = img
-                img = ops.ddpm_step(img, pred, noise("p_sample", shape, device, unet=unet_number, step=step, r=r), s, pred_objective,
-                                    sc, renoise=renoise, rn=rn)
-                if exists(self.step_hook):
-                    self.step_hook(dict(unet=unet_number, step=step, r=r, x_in=x_in, pred=pred, img=img))
-        ops.finalize_image(img, inpaint_images if has_inpainting else None, mask_u8)
-        if not self.auto_normalize_img:  # finalize_image un-normalises; undo for the (unused by the reference) raw mode
-            img = img * 2 - 1
-        return img
+    def stage_run(self, unet_number, shape, *, noise, lowres_cond_img=None, lowres_noise_level=None, text_embeds=None, text_mask=None,
+                  cond_images=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5, cond_scale=1.0):
+        """Prepare one cascade stage (x-independent conditioning, schedule tables, static buffers) and return its runner."""
+        return StageRun(self, unet_number, shape, noise=noise, lowres_cond_img=lowres_cond_img, lowres_noise_level=lowres_noise_level,
+                        text_embeds=text_embeds, text_mask=text_mask, cond_images=cond_images, inpaint_images=inpaint_images,
+                        inpaint_masks=inpaint_masks, inpaint_resample_times=inpaint_resample_times, cond_scale=cond_scale)
+
+    def p_sample_loop(self, unet_number, shape, **kwargs):
+        run = self.stage_run(unet_number, shape, **kwargs)
+        for step in range(run.num_steps):
+            for r in reversed(range(run.resample_times)):
+                run.step(step, r)
+        return run.finish()
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
@@ -281,10 +310,9 @@ class Imagen(nn.Module):
                                                float(la), float(lsig))
             shape = (batch_size, self.channels, image_size, image_size)
             img = self.p_sample_loop(
-                unet, shape, spec=spec, unet_number=unet_number, noise=noise, lowres_cond_img=lowres_cond_img,
-                lowres_noise_level=lowres_sample_noise_level, text_embeds=text_embeds, text_mask=text_masks, cond_images=cond_images,
-                inpaint_images=inpaint_images, inpaint_masks=inpaint_masks, inpaint_resample_times=inpaint_resample_times,
-                cond_scale=unet_cond_scale, pred_objective=pred_objective, dynamic_threshold=dynamic_threshold)
+                unet_number, shape, noise=noise, lowres_cond_img=lowres_cond_img, lowres_noise_level=lowres_sample_noise_level,
+                text_embeds=text_embeds, text_mask=text_masks, cond_images=cond_images, inpaint_images=inpaint_images,
+                inpaint_masks=inpaint_masks, inpaint_resample_times=inpaint_resample_times, cond_scale=unet_cond_scale)
             outputs.append(img)
             if exists(stop_at_unet_number) and stop_at_unet_number == unet_number:
                 break

@@ -17,6 +17,26 @@ ACT_NONE, ACT_SILU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
 PRED = {"noise": 0, "v": 1, "x_start": 2}
 
 launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+conv_profile = None  # bench.py sets this to a list: every tensor-core GEMM launch appends (flops, start_event, end_event)
+
+
+class _ConvTimer:
+    """CUDA-event bracket around one kd_conv_gemm launch on the launching stream (only active while profiling)."""
+
+    def __init__(self, flops):
+        self.flops = flops
+
+    def __enter__(self):
+        if conv_profile is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if conv_profile is not None:
+            self.e1.record()
+            conv_profile.append((self.flops, self.e0, self.e1))
+        return False
 
 
 def _stream():
@@ -78,13 +98,14 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
         _chk(addend_scale, torch.float32, "addend_scale")
         assert addend_scale.shape == (B, Cout)
     d = KdConvDesc(mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, 1 if out_f32 else 0, addend_f32)
-    check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
-                             _ptr(out), _stream()), "kd_conv_gemm")
+    with _ConvTimer(2.0 * B * H * W * Cout * taps * (Ca + Cb)):
+        check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
+                                 _ptr(out), _stream()), "kd_conv_gemm")
     _count()
     return out
 
 
-def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=None):
+def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=None, algo_k=None):
     """Plain GEMM y[M,N] = act(x[M,K] @ w[N,K]^T + bias) + addend on tensor cores (mode 2)."""
     _chk(x, torch.bfloat16, "x")
     _chk(w, torch.bfloat16, "w")
@@ -103,8 +124,9 @@ def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     d = KdConvDesc(2, 1, 1, M, K, 0, N, 1, act, 0, 1 if out_f32 else 0, addend_f32)
-    check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(x), None, _ptr(w), _ptr(bias), _ptr(addend), None, _ptr(out), _stream()),
-          "kd_conv_gemm(mode 2)")
+    with _ConvTimer(2.0 * M * N * (algo_k if algo_k is not None else K)):  # algo_k: un-padded K (algorithmic FLOPs)
+        check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(x), None, _ptr(w), _ptr(bias), _ptr(addend), None, _ptr(out), _stream()),
+              "kd_conv_gemm(mode 2)")
     _count()
     return out
 

@@ -133,6 +133,8 @@ class UnetExecutor:
             return _bf(W), Kp
 
         self.init_wx, self.init_kpx = pack_panel_w(x_idx)
+        # algorithmic (un-merged, un-padded) K per input channel, averaged over output channels: sum_k k^2 * cout_k / dim
+        self.init_algo_k = sum(c.kernel_size[0] ** 2 * c.out_channels for c in u.init_conv.convs) / self.dim
         self.n_fixed = len(fixed_idx)
         if self.n_fixed:
             self.init_wf, self.init_kpf = pack_panel_w(fixed_idx)
@@ -278,7 +280,7 @@ class UnetExecutor:
             b1 = min(B, b0 + chunk)
             panel = ops.im2col_nchw(img[b0:b1], self.init_ks, Kp)
             ops.gemm_rows(panel, w, bias, addend=None if addend is None else addend[b0:b1].view(-1, self.dim),
-                          out=out[b0:b1].view(-1, self.dim))
+                          out=out[b0:b1].view(-1, self.dim), algo_k=self.init_algo_k * img.shape[1])
             del panel
 
     # ------------------------------------------------------------------ blocks
