@@ -143,6 +143,7 @@ def test_sample_parity_base_stage(cuda_lib):
     errs = _per_step_unet_errors(pi, 1, ref_steps, 1, 4)
     worst = max(errs)
     print(f"base stage per-step (identical inputs) {[f'{e:.2e}' for e in errs]}; along own trajectory worst {traj:.2e}")
+    err = rel_l2(out, ref)
     print(f"base stage: final rel_l2 = {err:.3e}, worst per-step pred = {worst:.3e}")
     assert worst < TOL and err < TOL
 
