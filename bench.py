@@ -213,8 +213,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     prof, ops.conv_profile = ops.conv_profile, None
     imagen.use_cuda_graph = True
-    conv_flops = sum(f for f, _, _ in prof)
-    conv_ms = sum(a.elapsed_time(b) for _, a, b in prof)
+    conv_flops = sum(p[0] for p in prof)
+    conv_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
     achieved = conv_flops / (conv_ms / 1e3) / 1e12
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=achieved / peaks["tf_sustained"],
                     traffic=None, kernel="conv_gemm_kernel (tcgen05 implicit GEMM)", launches_per_step=len(prof),

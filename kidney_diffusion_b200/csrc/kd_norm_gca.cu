@@ -56,29 +56,38 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long HW, int C, int 
   }
 }
 
+// one warp per (b, group): lanes stride over the per-block partials, then a fixed-order shuffle tree (deterministic)
 __global__ void gn_finalize_kernel(const float* __restrict__ pa, int nblk_a, float scale_a, const float* __restrict__ pb,
                                    int nblk_b, float scale_b, int G, double count, float eps, float* __restrict__ mean_rstd) {
   const int b = blockIdx.x;
-  const int g = threadIdx.x;
+  const int g = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   if (g >= G) return;
   double s = 0.0, ss = 0.0;
-  for (int k = 0; k < nblk_a; ++k) {
-    const float* q = pa + (((long)b * nblk_a + k) * G + g) * 2;
-    s += (double)q[0] * scale_a;
-    ss += (double)q[1] * scale_a * scale_a;
+  for (int k = lane; k < nblk_a; k += 32) {
+    const float2 q = *reinterpret_cast<const float2*>(pa + (((long)b * nblk_a + k) * G + g) * 2);
+    s += (double)q.x * scale_a;
+    ss += (double)q.y * scale_a * scale_a;
   }
   if (pb != nullptr) {
-    for (int k = 0; k < nblk_b; ++k) {
-      const float* q = pb + (((long)b * nblk_b + k) * G + g) * 2;
-      s += (double)q[0] * scale_b;
-      ss += (double)q[1] * scale_b * scale_b;
+    for (int k = lane; k < nblk_b; k += 32) {
+      const float2 q = *reinterpret_cast<const float2*>(pb + (((long)b * nblk_b + k) * G + g) * 2);
+      s += (double)q.x * scale_b;
+      ss += (double)q.y * scale_b * scale_b;
     }
   }
-  const double mean = s / count;
-  double var = ss / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_rstd[((long)b * G + g) * 2] = (float)mean;
-  mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[((long)b * G + g) * 2] = (float)mean;
+    mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long HW, int C, int c_offset, int group_size,
@@ -217,20 +226,57 @@ __global__ void gca_pool_kernel(const bf16* __restrict__ x, const float* __restr
   }
 }
 
+// block = 256 channels of one batch element: the per-chunk rescale factors exp(m_k - M) are computed once into smem
 __global__ void gca_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ml, int nblk, int C,
                                     float* __restrict__ pooled) {
+  extern __shared__ float f[];  // [nblk]
+  __shared__ float s_red[8];
+  __shared__ float s_M, s_L;
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  float M = -INFINITY;
-  for (int k = 0; k < nblk; ++k) M = fmaxf(M, ml[((long)b * nblk + k) * 2]);
-  float L = 0.f, s = 0.f;
-  for (int k = 0; k < nblk; ++k) {
-    const float mk = ml[((long)b * nblk + k) * 2];
-    const float f = (mk == -INFINITY) ? 0.f : __expf(mk - M);
-    L += f * ml[((long)b * nblk + k) * 2 + 1];
-    if (c < C) s += f * part[((long)b * nblk + k) * C + c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* mlb = ml + (long)b * nblk * 2;
+  float m = -INFINITY;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) m = fmaxf(m, mlb[k * 2]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = -INFINITY;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mm = fmaxf(mm, s_red[i]);
+    s_M = mm;
   }
-  if (c < C) pooled[(long)b * C + c] = s / L;
+  __syncthreads();
+  const float M = s_M;
+  float l = 0.f;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    const float mk = mlb[k * 2];
+    const float fk = (mk == -INFINITY) ? 0.f : __expf(mk - M);
+    f[k] = fk;
+    l += fk * mlb[k * 2 + 1];
+  }
+  l = warp_sum(l);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ll = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) ll += s_red[i];
+    s_L = ll;
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const float* pp = part + (long)b * nblk * C + c;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= nblk; k += 4) {
+    s0 = fmaf(f[k], pp[(long)k * C], s0);
+    s1 = fmaf(f[k + 1], pp[(long)(k + 1) * C], s1);
+    s2 = fmaf(f[k + 2], pp[(long)(k + 2) * C], s2);
+    s3 = fmaf(f[k + 3], pp[(long)(k + 3) * C], s3);
+  }
+  for (; k < nblk; ++k) s0 = fmaf(f[k], pp[(long)k * C], s0);
+  pooled[(long)b * C + c] = ((s0 + s1) + (s2 + s3)) / s_L;
 }
 
 __global__ void gate_residual_kernel(const bf16* __restrict__ h, const float* __restrict__ gate, const bf16* __restrict__ res,
@@ -366,7 +412,7 @@ extern "C" int kd_gn_finalize(const float* partial_a, int nblk_a, float scale_a,
                               int B, int num_groups, double count, float eps, float* mean_rstd, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(partial_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && count > 0, "kd_gn_finalize: bad argument");
-  gn_finalize_kernel<<<B, 32, 0, stream>>>(partial_a, nblk_a, scale_a, partial_b, nblk_b, scale_b, num_groups, count, eps, mean_rstd);
+  gn_finalize_kernel<<<B, 32 * num_groups, 0, stream>>>(partial_a, nblk_a, scale_a, partial_b, nblk_b, scale_b, num_groups, count, eps, mean_rstd);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -418,7 +464,8 @@ extern "C" int kd_gca_pool(const void* x, const float* logits, int B, long HW, i
 extern "C" int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(part && ml && pooled && B > 0 && nblk > 0 && C > 0, "kd_gca_finalize: bad argument");
-  gca_finalize_kernel<<<dim3(kd_ceil_div(C, 128), B), 128, 0, stream>>>(part, ml, nblk, C, pooled);
+  KD_REQUIRE(nblk <= 8192, "kd_gca_finalize: nblk too large");
+  gca_finalize_kernel<<<dim3(kd_ceil_div(C, 256), B), 256, nblk * sizeof(float), stream>>>(part, ml, nblk, C, pooled);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

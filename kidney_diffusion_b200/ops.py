@@ -23,8 +23,8 @@ conv_profile = None  # bench.py sets this to a list: every tensor-core GEMM laun
 class _ConvTimer:
     """CUDA-event bracket around one kd_conv_gemm launch on the launching stream (only active while profiling)."""
 
-    def __init__(self, flops):
-        self.flops = flops
+    def __init__(self, flops, label=None):
+        self.flops, self.label = flops, label
 
     def __enter__(self):
         if conv_profile is not None:
@@ -35,7 +35,7 @@ class _ConvTimer:
     def __exit__(self, *exc):
         if conv_profile is not None:
             self.e1.record()
-            conv_profile.append((self.flops, self.e0, self.e1))
+            conv_profile.append((self.flops, self.e0, self.e1, self.label))
         return False
 
 
@@ -98,7 +98,7 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
         _chk(addend_scale, torch.float32, "addend_scale")
         assert addend_scale.shape == (B, Cout)
     d = KdConvDesc(mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, 1 if out_f32 else 0, addend_f32)
-    with _ConvTimer(2.0 * B * H * W * Cout * taps * (Ca + Cb)):
+    with _ConvTimer(2.0 * B * H * W * Cout * taps * (Ca + Cb), (mode, B, H, W, Ca + Cb, Cout, ksize if mode == 0 else 2)):
         check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
                                  _ptr(out), _stream()), "kd_conv_gemm")
     _count()
@@ -124,7 +124,7 @@ def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     d = KdConvDesc(2, 1, 1, M, K, 0, N, 1, act, 0, 1 if out_f32 else 0, addend_f32)
-    with _ConvTimer(2.0 * M * N * (algo_k if algo_k is not None else K)):  # algo_k: un-padded K (algorithmic FLOPs)
+    with _ConvTimer(2.0 * M * N * (algo_k if algo_k is not None else K), (2, 1, 1, M, K, N, 1)):  # algo_k: un-padded K (algorithmic FLOPs)
         check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(x), None, _ptr(w), _ptr(bias), _ptr(addend), None, _ptr(out), _stream()),
               "kd_conv_gemm(mode 2)")
     _count()

@@ -32,3 +32,22 @@ run.step(2)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("launches in profiled step:", ops.launch_count - n0)
+
+if os.environ.get("KD_CONV_TABLE"):
+    import collections
+
+    ops.conv_profile = []
+    run.step(3)
+    torch.cuda.synchronize()
+    prof, ops.conv_profile = ops.conv_profile, None
+    agg = collections.OrderedDict()
+    for flops, e0, e1, label in prof:
+        a = agg.setdefault(label, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += flops
+        a[2] += e0.elapsed_time(e1)
+    print("mode B H W Cin Cout k | launches | GFLOP each | ms each | TFLOP/s")
+    for label, (n, fl, ms) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+        print(f"{label} | {n:3d} | {fl / n / 1e9:8.1f} | {ms / n:7.3f} | {fl / ms / 1e9:7.1f}")
+    tot_f, tot_ms = sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values())
+    print(f"total conv: {tot_f / 1e12:.3f} TFLOP in {tot_ms:.2f} ms = {tot_f / tot_ms / 1e9:.1f} TFLOP/s")
