@@ -161,10 +161,14 @@ int kd_q_sample(const float* x0, const float* noise, float alpha, float sigma, f
 int kd_randn(float* out, long n, uint64_t seed, uint64_t key, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ K8: overlap-border pack for the patch-grid sampler
- * replaces: the inpaint canvas construction of generate_image_distributed (sample_ultra_res.py:149-170): copies the
- *           overlap strips of up to three finished neighbour patches into inpaint_patch / inpaint_mask. */
-int kd_border_pack(float* inpaint /* [3,S,S] */, uint8_t* mask /* [S,S] */, const float* above, const float* side,
-                   const float* corner /* each [3,S,S] or NULL */, int S, int overlap_pos, int orientation, kd_stream_t stream);
+ * replaces: the inpaint canvas construction of generate_image_distributed (sample_ultra_res.py:149-170): writes the overlap
+ *           strips of up to three finished neighbour patches into inpaint_patch [3,S,S] / inpaint_mask [S,S] (write order
+ *           above -> side -> corner; the corner sets no mask bits).  Each neighbour is a strided strip view
+ *           (element (c,y,x) = ptr[c*cs + y*rs + x]): above = bottom `overlap_pos` rows [3,ov,S], side = facing columns
+ *           [3,S,ov], corner = facing box [3,ov,ov]; a full resident patch and a strip received over NVLink use the same call. */
+int kd_border_pack(float* inpaint, uint8_t* mask, const float* above, long above_cs, long above_rs, const float* side, long side_cs,
+                   long side_rs, const float* corner, long corner_cs, long corner_rs, int S, int overlap_pos, int orientation,
+                   kd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ SIGNATURES = {
     "kd_finalize_image": (c_int, [_P, _P, _P, _I, _I, _L, _P]),
     "kd_q_sample": (c_int, [_P, _P, _F, _F, _P, _L, _P]),
     "kd_randn": (c_int, [_P, _L, c_uint64, c_uint64, _P]),
-    "kd_border_pack": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "kd_border_pack": (c_int, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -206,28 +206,38 @@ __global__ void randn_kernel(float* __restrict__ out, long n, uint64_t seed, uin
 
 // ------------------------------------------------------------------------------------------------ K8: border pack
 // sample_ultra_res.py:149-170 -- write order above -> side -> corner; the corner sets no mask bits of its own.
-__global__ void border_pack_kernel(float* __restrict__ inpaint, uint8_t* __restrict__ mask, const float* __restrict__ above,
-                                   const float* __restrict__ side, const float* __restrict__ corner, int S, int ov, int orientation) {
+// Each neighbour is given as a STRIP view: element (c, y, x) of the strip = ptr[c * cs + y * rs + x], where
+//   above  strip = the neighbour's bottom `ov` rows            [3, ov, S]
+//   side   strip = the neighbour's `ov` columns facing us      [3, S, ov]
+//   corner strip = the diagonal neighbour's facing ov x ov box [3, ov, ov]
+// so the same kernel reads either a full resident patch (cs = S*S, rs = S, pointer offset to the strip origin) or a
+// contiguous strip received from another rank over NVLink.
+struct Strip {
+  const float* p;
+  long cs, rs;
+};
+
+__global__ void border_pack_kernel(float* __restrict__ inpaint, uint8_t* __restrict__ mask, Strip above, Strip side, Strip corner,
+                                   int S, int ov, int orientation) {
   const long n = (long)S * S;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int y = (int)(i / S), x = (int)(i % S);
     const bool in_top = y < ov;
     const bool in_side = orientation == -1 ? (x < ov) : (x >= S - ov);
-    // source column inside the neighbour for the side / corner strips
-    const int sx = orientation == -1 ? (S - ov + x) : (x - (S - ov));
+    const int sx = orientation == -1 ? x : (x - (S - ov));  // column inside the side / corner strip
     uint8_t m = 0;
     float v[3] = {0.f, 0.f, 0.f};
-    if (above && in_top) {
+    if (above.p && in_top) {
       m = 1;
-      for (int c = 0; c < 3; ++c) v[c] = above[(long)c * n + (long)(S - ov + y) * S + x];
+      for (int c = 0; c < 3; ++c) v[c] = above.p[c * above.cs + (long)y * above.rs + x];
     }
-    if (side && in_side) {
+    if (side.p && in_side) {
       m = 1;
-      for (int c = 0; c < 3; ++c) v[c] = side[(long)c * n + (long)y * S + sx];
+      for (int c = 0; c < 3; ++c) v[c] = side.p[c * side.cs + (long)y * side.rs + sx];
     }
-    if (corner && in_top && in_side)
-      for (int c = 0; c < 3; ++c) v[c] = corner[(long)c * n + (long)(S - ov + y) * S + sx];
+    if (corner.p && in_top && in_side)
+      for (int c = 0; c < 3; ++c) v[c] = corner.p[c * corner.cs + (long)y * corner.rs + sx];
     for (int c = 0; c < 3; ++c) inpaint[(long)c * n + i] = v[c];
     mask[i] = m;
   }
@@ -319,12 +329,14 @@ extern "C" int kd_randn(float* out, long n, uint64_t seed, uint64_t key, kd_stre
   return KD_OK;
 }
 
-extern "C" int kd_border_pack(float* inpaint, uint8_t* mask, const float* above, const float* side, const float* corner, int S,
-                              int overlap_pos, int orientation, kd_stream_t stream_) {
+extern "C" int kd_border_pack(float* inpaint, uint8_t* mask, const float* above, long above_cs, long above_rs, const float* side,
+                              long side_cs, long side_rs, const float* corner, long corner_cs, long corner_rs, int S, int overlap_pos,
+                              int orientation, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(inpaint && mask && S > 0 && overlap_pos >= 0 && overlap_pos <= S && (orientation == 1 || orientation == -1),
+  KD_REQUIRE(inpaint && mask && S > 0 && overlap_pos > 0 && overlap_pos <= S && (orientation == 1 || orientation == -1),
              "kd_border_pack: bad argument");
-  border_pack_kernel<<<ew_blocks((long)S * S), 256, 0, stream>>>(inpaint, mask, above, side, corner, S, overlap_pos, orientation);
+  Strip a{above, above_cs, above_rs}, sd{side, side_cs, side_rs}, c{corner, corner_cs, corner_rs};
+  border_pack_kernel<<<ew_blocks((long)S * S), 256, 0, stream>>>(inpaint, mask, a, sd, c, S, overlap_pos, orientation);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

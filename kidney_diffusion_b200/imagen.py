@@ -44,14 +44,25 @@ class NoiseSchedulerSpec(nn.Module):
 class CounterNoise:
     """Counter-based noise: every randn site of the sampler is keyed by (seed, stream key, unet, step, r, site), so
     results are identical for any GPU count / patch-to-rank assignment (SURVEY.md section 8e invariance requirement).
+    ``stream_key`` is one int for the whole batch or a list with one key per batch element (the patch-grid sampler keys
+    each patch by its index so that batching patches never changes a patch's noise).
     The reference draws from the unseeded global torch generator; tests inject identical tensors into both paths."""
 
     def __init__(self, seed=0, stream_key=0):
         self.seed, self.stream_key = seed, stream_key
 
+    @staticmethod
+    def _key(stream_key, unet, step, r, site):
+        return zlib.crc32(f"{stream_key}/{unet}/{step}/{r}/{SITES[site]}".encode()) | (SITES[site] << 40) | (unet << 48)
+
     def __call__(self, site, shape, device, unet=0, step=0, r=0):
-        key = zlib.crc32(f"{self.stream_key}/{unet}/{step}/{r}/{SITES[site]}".encode()) | (SITES[site] << 40) | (unet << 48)
-        return ops.randn(shape, self.seed, key, device)
+        if isinstance(self.stream_key, (list, tuple)):
+            assert len(self.stream_key) == shape[0]
+            out = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+            for b, k in enumerate(self.stream_key):
+                ops.randn_into(out[b], self.seed, self._key(k, unet, step, r, site))
+            return out
+        return ops.randn(shape, self.seed, self._key(self.stream_key, unet, step, r, site), device)
 
 
 class _StepGraph:

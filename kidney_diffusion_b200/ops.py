@@ -167,7 +167,9 @@ def _nblk(HW, C, B):
     oct_ = C // 8
     threads = 256 if oct_ >= 256 else (256 // oct_) * oct_
     lanes = max(1, threads // oct_)
-    want = max(1, (148 * 4) // max(B, 1))
+    # independent of the batch size on purpose: a sample's reduction order (hence its bits) must not depend on which
+    # other patches share its batch (patch-grid invariance across GPU counts)
+    want = 148 * 2
     return int(max(1, min(want, -(-HW // lanes))))
 
 
@@ -385,10 +387,37 @@ def randn(shape, seed, key, device):
     return out
 
 
+def neighbour_strips(S, ov, orientation, above=None, side=None, corner=None):
+    """Strip views (tensor, channel stride, row stride) into FULL neighbour patches [3,S,S] (sample_ultra_res.py:156-170)."""
+    def view(t, y0, x0):
+        if t is None:
+            return None
+        assert t.shape[-3:] == (3, S, S) and t.is_contiguous()
+        t3 = t.reshape(3, S, S)
+        return (t3[:, y0:, x0:], S * S, S)
+    side_x0 = S - ov if orientation == -1 else 0  # o=-1: neighbour's right columns face us; o=+1: its left columns
+    return view(above, S - ov, 0), view(side, 0, side_x0), view(corner, S - ov, side_x0)
+
+
+def randn_into(out, seed, key):
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.is_cuda
+    check(lib().kd_randn(_ptr(out), out.numel(), seed & (2**64 - 1), key & (2**64 - 1), _stream()), "kd_randn")
+    _count()
+    return out
+
+
 def border_pack(S, overlap_pos, orientation, above, side, corner, device):
+    """above / side / corner: None or (tensor_view, channel_stride, row_stride) strips (see neighbour_strips) -> (inpaint, mask)."""
     inpaint = torch.empty((3, S, S), device=device, dtype=torch.float32)
     mask = torch.empty((S, S), device=device, dtype=torch.uint8)
-    check(lib().kd_border_pack(_ptr(inpaint), _ptr(mask), _ptr(above), _ptr(side), _ptr(corner), S, overlap_pos, orientation,
-                               _stream()), "kd_border_pack")
+    args = []
+    for st in (above, side, corner):
+        if st is None:
+            args += [None, 0, 0]
+        else:
+            t, cs, rs = st
+            assert t.dtype == torch.float32 and t.is_cuda
+            args += [_ptr(t), cs, rs]
+    check(lib().kd_border_pack(_ptr(inpaint), _ptr(mask), *args, S, overlap_pos, orientation, _stream()), "kd_border_pack")
     _count()
     return inpaint, mask

@@ -475,5 +475,11 @@ def test_border_pack_matches_reference_layout(cuda_lib, orientation):
             else:
                 ip[:, :ov, -ov:] = c[:, -ov:, :ov]
         dev = lambda t: None if t is None else t.to(DEV)
-        op, om = ops.border_pack(S, ov, orientation, dev(a), dev(n), dev(c), DEV)
+        # (1) strips as views into full resident patches
+        sa, ss, sc = ops.neighbour_strips(S, ov, orientation, dev(a), dev(n), dev(c))
+        op, om = ops.border_pack(S, ov, orientation, sa, ss, sc, DEV)
         assert torch.equal(op.cpu(), ip) and torch.equal(om.cpu().float(), im)
+        # (2) contiguous strips, as received from another rank
+        cont = lambda st: None if st is None else (st[0].contiguous(), st[0].shape[1] * st[0].shape[2], st[0].shape[2])
+        op2, om2 = ops.border_pack(S, ov, orientation, cont(sa), cont(ss), cont(sc), DEV)
+        assert torch.equal(op2.cpu(), ip) and torch.equal(om2.cpu().float(), im)
