@@ -73,6 +73,10 @@ typedef struct KdConvDesc {
   int addend_f32;   /* dtype of addend (same layout as out) */
 } KdConvDesc;
 
+/* Test / profiling hook: 0 = automatic kernel choice (default), 1 = force the single-CTA 128x128 kernel, 2 = force the
+ * CTA-pair (cta_group::2) kernel.  Both kernels accumulate each output in the same k order: results are bit-identical. */
+int kd_set_conv_impl(int impl);
+
 int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
                  const void* w /* bf16 [Cout, taps*(Ca+Cb)], K ordered (tap, channel) */, const float* bias /* [Cout] or NULL */,
                  const void* addend /* or NULL */, const float* addend_scale /* [B,Cout] or NULL (=1) */, void* out,

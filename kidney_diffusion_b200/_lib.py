@@ -34,6 +34,7 @@ SIGNATURES = {
     "kd_version": (c_int, []),
     "kd_last_error": (c_char_p, []),
     "kd_check_device": (c_int, []),
+    "kd_set_conv_impl": (c_int, [_I]),
     "kd_conv_gemm": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "kd_linear_small": (c_int, [_P, _I, _I, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
     "kd_sinu_emb": (c_int, [_P, _P, _I, _I, _P, _P]),

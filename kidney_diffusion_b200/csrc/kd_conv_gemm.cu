@@ -317,6 +317,295 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ================================================================================================ conv v2
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN output tile with UMMA M = 256.
+// Each CTA loads only its own 128 A rows and its own half (BN/2 rows) of the weight tile, and the pair's tensor cores
+// read both halves -- this halves the per-SM operand feed from L2, which is what bounded the single-CTA kernel
+// (32 KB per k-block at ~64 B/clk/SM = 512 cycles against 256 cycles of MMA).  CTAs are persistent (static round-robin
+// tile scheduler) and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+//
+// Barrier protocol (identical smem layout in both CTAs; "leader" = cluster rank 0):
+//   full[s]      leader only, count 2: leader producer's arrive.expect_tx(bytes of BOTH CTAs) + peer producer's remote
+//                arrive; all four TMA loads of a stage complete_tx on the leader's barrier (.cta_group::2 loads).
+//   empty[s]     both CTAs, count 1: tcgen05.commit multicast from the leader's MMA thread.
+//   tmem_full[a] both CTAs, count 1: commit multicast after the last k-block of a tile.
+//   tmem_empty[a] leader only, count 8: one elected lane of each of the 4 epilogue warps of both CTAs (remote arrive).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_remote_arrive(uint32_t local_bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32  remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64  _, [remAddr32];\n\t"
+      "}" ::"r"(local_bar),
+      "r"(cta_rank)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+constexpr int NUM_THREADS2 = 256;
+
+// epilogue of one 32-column chunk of one accumulator row (shared by both kernels' store paths)
+__device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const uint32_t* acc, int nc, int b, int h, int w) {
+  const int Cq = p.Cout >> 2;
+  long long out_off;
+  if (p.out_mode == 1) {
+    const int q4 = nc / Cq, c = nc - q4 * Cq;
+    const int dy = q4 >> 1, dx = q4 & 1;
+    out_off = (((long long)b * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * Cq + c;
+  } else {
+    out_off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc;
+  }
+  const float* gate = p.addend_scale ? p.addend_scale + (long long)b * p.Cout + nc : nullptr;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (nc + g * 8 + 8 > p.Cout) break;
+    float v[8];
+    if (p.bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + g * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + g * 8 + 4));
+      v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + v[j], p.act);
+    if (p.addend != nullptr) {
+      float a[8];
+      if (p.addend_f32) {
+        const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + out_off + g * 8);
+        float4 a0 = ap[0], a1 = ap[1];
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      } else {
+        bf16x8 raw = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.addend) + out_off + g * 8);
+        bf16x8_to_float(raw, a);
+      }
+      if (gate != nullptr) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gate + g * 8 + 4);
+        a[0] *= g0.x; a[1] *= g0.y; a[2] *= g0.z; a[3] *= g0.w; a[4] *= g1.x; a[5] *= g1.y; a[6] *= g1.z; a[7] *= g1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += a[j];
+    }
+    if (p.out_f32) {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + g * 8);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]);
+      op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.out) + out_off + g * 8) = float_to_bf16x8(v);
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_w, const ConvParams p, const int num_pair_tiles) {
+  constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  // instruction descriptor: D fp32, A = B = bf16, K-major, N = BN, M = 256 (pair)
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  cluster_sync_all();  // both CTAs are resident before the pair-wide TMEM allocation
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    if (p.Cb > 0) tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 2);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs, one lane each)
+    if (lane == 0) {
+      const int pad = (p.mode == 0) ? (p.ksize >> 1) : 0;
+      uint32_t it = 0;
+      for (int t = cluster_id; t < num_pair_tiles; t += num_clusters) {
+        const int n_tile = t % p.n_tiles;
+        int m_tile = (t / p.n_tiles) * 2 + (int)rank;
+        const int tile_w = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int tile_h = m_tile % p.tiles_h;
+        const int tile_b = m_tile / p.tiles_h;  // may be == tiles_b for the odd tail: TMA zero-fills, epilogue masks
+        const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, b0 = tile_b * p.TB;
+        const int n0 = n_tile * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb_local = smem_u32(&full_bar[s]);
+          const uint32_t fb_leader = fb_local & kPeerBitMask;
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * STAGE_BYTES);
+          const int tap = kb / p.chunks_per_tap;
+          const int ch = kb - tap * p.chunks_per_tap;
+          const bool src_b = ch >= p.chunks_a;
+          const CUtensorMap* map = src_b ? &map_b : &map_a;
+          const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+          if (p.mode == 1) {
+            const int dy = tap >> 1, dx = tap & 1;
+            const int C = src_b ? p.Cb : p.Ca;
+            tma_load_5d_2sm(a_dst, map, fb_leader, dx * C + c0, w0, dy, h0, b0);
+          } else {
+            const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+            tma_load_5d_2sm(a_dst, map, fb_leader, c0, w0 + kx - pad, h0 + ky - pad, b0, 0);
+          }
+          tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, fb_leader, kb * BK, n0);
+          if (rank != 0) mbar_remote_arrive(fb_local, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA, one lane)
+    if (rank == 0 && lane == 0) {
+      uint32_t it = 0, tile_iter = 0;
+      for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
+        const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+          const uint64_t a_desc = make_sw128_desc(a_addr);
+          const uint64_t b_desc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(smem_u32(&empty_bar[s]));
+        }
+        umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue (both CTAs): own 128 rows x BN columns
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int tw = r % p.TW;
+    const int th = (r / p.TW) % p.TH;
+    const int tb = r / (p.TW * p.TH);
+    uint32_t tile_iter = 0;
+    for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
+      const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+      const int n_tile = t % p.n_tiles;
+      int m_tile = (t / p.n_tiles) * 2 + (int)rank;
+      const int tile_w = m_tile % p.tiles_w;
+      m_tile /= p.tiles_w;
+      const int tile_h = m_tile % p.tiles_h;
+      const int tile_b = m_tile / p.tiles_h;
+      const int b = tile_b * p.TB + tb, h = tile_h * p.TH + th, w = tile_w * p.TW + tw;
+      const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
+      const int n0 = n_tile * BN;
+
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
+        tmem_ld_wait();
+        const int nc = n0 + chunk * 32;
+        if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_remote_arrive(smem_u32(&tmem_empty_bar[as]), 0);  // accumulator stage drained (leader's barrier)
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its partner can still signal its barriers / read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -398,7 +687,38 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, 
   return KD_OK;
 }
 
+
+template <int BN, int STAGES>
+int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool configured = false;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured) {
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured = true;
+    }
+  }
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  const long long pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+  KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
+  int clusters = kd_num_sms() / 2;
+  if (pair_tiles < clusters) clusters = (int)pair_tiles;
+  conv_gemm_pair_kernel<BN, STAGES><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, p, (int)pair_tiles);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel (kd_set_conv_impl)
+
 }  // namespace
+
+extern "C" int kd_set_conv_impl(int impl) {
+  if (impl < 0 || impl > 2) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0, 1 or 2");
+  g_conv_impl = impl;
+  return KD_OK;
+}
 
 extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
                             const void* addend, const float* addend_scale, void* out, kd_stream_t stream_) {
@@ -435,7 +755,10 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
   p.num_kb = taps * p.chunks_per_tap;
   p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out;
 
-  const int BN = d->Cout >= 128 ? 128 : 64;
+  // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel
+  const bool use_pair = (g_conv_impl == 2) || (g_conv_impl == 0 && d->Cout >= 128);
+  KD_REQUIRE(!(g_conv_impl == 2 && d->Cout < 128), "kd_conv_gemm: the CTA-pair kernel needs Cout >= 128");
+  const int BN = use_pair ? (d->Cout >= 256 ? 256 : 128) : (d->Cout >= 128 ? 128 : 64);
   p.n_tiles = kd_ceil_div(d->Cout, BN);
   const long long grid = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   KD_REQUIRE(grid > 0 && grid < 2147483647LL, "kd_conv_gemm: grid too large");
@@ -455,9 +778,13 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
     const uint64_t Ktot = (uint64_t)taps * (d->Ca + d->Cb);
     const uint64_t dims[2] = {Ktot, (uint64_t)d->Cout};
     const uint64_t str[1] = {Ktot * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};  // pair kernel: each CTA loads half the tile rows
     rc = encode_map(&mw, w, 2, dims, str, box);
     if (rc) return rc;
+  }
+  if (use_pair) {
+    if (BN == 256) return launch_pair<256, 6>(ma, mb, mw, p, stream);
+    return launch_pair<128, 8>(ma, mb, mw, p, stream);
   }
   if (BN == 128) return launch<128, 3>(ma, mb, mw, p, grid, stream);
   return launch<64, 4>(ma, mb, mw, p, grid, stream);

@@ -70,6 +70,11 @@ def lib():
 
 
 # ------------------------------------------------------------------------------------------------ K1 conv / GEMM
+def set_conv_impl(impl):
+    """0 = automatic (default), 1 = single-CTA 128x128 kernel, 2 = CTA-pair cta_group::2 kernel (tests / profiling)."""
+    check(lib().kd_set_conv_impl(int(impl)), "kd_set_conv_impl")
+
+
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
               addend=None, addend_scale=None, out=None):
     """xa / xb: NHWC bf16 [B,H,W,C]; w: packed bf16 [Cout, taps*(Ca+Cb)]; returns NHWC (bf16 or fp32)."""

@@ -70,6 +70,32 @@ def test_conv_gemm_matches_conv2d(cuda_lib, B, H, W, Cin, Cout, k):
     assert err < 5e-3
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(1, 64, 64, 256, 256, 3), (3, 24, 40, 128, 640, 1), (2, 16, 16, 64, 128, 3), (1, 8, 8, 1024, 1024, 3),
+                                               (5, 8, 8, 128, 384, 3), (1, 128, 128, 128, 128, 3)])
+def test_conv_pair_kernel_bit_identical_to_single_cta_kernel(cuda_lib, B, H, W, Cin, Cout, k):
+    """cta_group::2 persistent kernel vs the single-CTA kernel: same k order per output -> identical bits; odd tile counts,
+    N tails (640 = 2.5 x 256) and multi-tile-per-CTA persistence are all exercised."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    add = torch.randn(B, Cout, H, W, generator=g)
+    dx, dw, db, da = nhwc(x), pack_w(w), b.to(DEV), nhwc(add)
+    try:
+        ops.set_conv_impl(1)
+        ref = ops.conv_gemm(dx, dw, db, ksize=k, act=ops.ACT_SILU, addend=da)
+        ops.set_conv_impl(2)
+        out = ops.conv_gemm(dx, dw, db, ksize=k, act=ops.ACT_SILU, addend=da)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_impl(0)
+    assert torch.equal(out, ref)
+    err = rel_l2(from_nhwc(out), F.silu(F.conv2d(rb(x), rb(w), b, padding=k // 2)) + rb(add))
+    assert err < 5e-3
+
+
 def test_conv_gemm_two_sources_act_addend_gate(cuda_lib):
     from kidney_diffusion_b200 import ops
 
