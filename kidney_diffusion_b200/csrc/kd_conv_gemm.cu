@@ -390,7 +390,23 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                : "memory");
 }
 
+// TMA tensor store smem -> global (bulk async group), used by the coalesced epilogue
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
 constexpr int NUM_THREADS2 = 256;
+constexpr int EPI_COLS = 64;                          // columns per staged group = one 128-byte swizzle row of bf16
+constexpr int EPI_STAGE_BYTES = BM * EPI_COLS * 2;    // 16 KB per staging buffer, two buffers
 
 // epilogue of one 32-column chunk of one accumulator row (shared by both kernels' store paths)
 __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const uint32_t* acc, int nc, int b, int h, int w) {
@@ -449,7 +465,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_w, const ConvParams p, const int num_pair_tiles) {
+                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const ConvParams p,
+                      const int num_pair_tiles) {
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
@@ -459,7 +476,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES;
+  const uint32_t epi_smem = smem_base + STAGES * STAGE_BYTES;  // 2 x 16 KB swizzled output staging (1024-aligned)
+  uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -476,6 +494,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_out);
     if (p.Cb > 0) tma_prefetch_desc(&map_b);
   }
   if (warp == 1 && lane == 0) {
@@ -569,7 +588,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int tw = r % p.TW;
     const int th = (r / p.TW) % p.TH;
     const int tb = r / (p.TW * p.TH);
-    uint32_t tile_iter = 0;
+    uint32_t tile_iter = 0, epi_it = 0;
     for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
       const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
       const int n_tile = t % p.n_tiles;
@@ -584,18 +603,102 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
       tc_fence_after();
+      if (p.out_f32) {
+        // fp32 output (tests / small tensors): direct per-row stores
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
-        tmem_ld_wait();
-        const int nc = n0 + chunk * 32;
-        if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
+          tmem_ld_wait();
+          const int nc = n0 + chunk * 32;
+          if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
+        }
+      } else {
+        // bf16 output: 64-column groups staged in 128B-swizzled smem and written with one coalesced TMA store each
+        const bool tile_in_range = tile_b < p.tiles_b;
+        const int Cq = p.Cout >> 2;
+#pragma unroll 1
+        for (int g = 0; g < BN / EPI_COLS; ++g, ++epi_it) {
+          const int nc0 = n0 + g * EPI_COLS;
+          if (nc0 >= p.Cout) break;  // uniform across the CTA
+          const uint32_t stage = epi_smem + (epi_it & 1) * EPI_STAGE_BYTES;
+          // the TMA store that last read this staging buffer (two groups ago) must have finished reading it
+          if (warp == 4 && lane == 0) tma_store_wait_read<1>();
+          epi_barrier();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + half * 32), acc);
+            tmem_ld_wait();
+            const int nc = nc0 + half * 32;
+            const float* gate = p.addend_scale ? p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc : nullptr;
+            long long add_off = 0;
+            if (p.addend != nullptr && row_ok) {
+              if (p.out_mode == 1) {
+                const int q4 = nc / Cq, c = nc - q4 * Cq;
+                add_off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
+              } else {
+                add_off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 4 groups of 8 columns -> one 16-byte staging store each
+              float v[8];
+              if (p.bias != nullptr && nc + q * 8 + 8 <= p.Cout) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + q * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + q * 8 + 4));
+                v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[q * 8 + j]) + v[j], p.act);
+              if (p.addend != nullptr && row_ok && nc + q * 8 + 8 <= p.Cout) {
+                float a[8];
+                if (p.addend_f32) {
+                  const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + add_off + q * 8);
+                  float4 a0 = ap[0], a1 = ap[1];
+                  a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                } else {
+                  bf16x8 raw = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.addend) + add_off + q * 8);
+                  bf16x8_to_float(raw, a);
+                }
+                if (gate != nullptr) {
+                  const float4 g0 = *reinterpret_cast<const float4*>(gate + q * 8);
+                  const float4 g1 = *reinterpret_cast<const float4*>(gate + q * 8 + 4);
+                  a[0] *= g0.x; a[1] *= g0.y; a[2] *= g0.z; a[3] *= g0.w; a[4] *= g1.x; a[5] *= g1.y; a[6] *= g1.z; a[7] *= g1.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += a[j];
+              }
+              const uint32_t chunk16 = (uint32_t)(half * 4 + q);
+              const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
+              const bf16x8 o8 = float_to_bf16x8(v);
+              const int4 ov = *reinterpret_cast<const int4*>(&o8);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z), "r"(ov.w) : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          epi_barrier();
+          if (warp == 4 && lane == 0) {
+            if (tile_in_range) {
+              if (p.out_mode == 1) {
+                const int q4 = nc0 / Cq, c0 = nc0 - q4 * Cq;
+                tma_store_5d(&map_out, stage, (q4 & 1) * Cq + c0, tile_w * p.TW, q4 >> 1, tile_h * p.TH, tile_b * p.TB);
+              } else {
+                tma_store_5d(&map_out, stage, nc0, tile_w * p.TW, tile_h * p.TH, tile_b * p.TB, 0);
+              }
+            }
+            tma_store_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_remote_arrive(smem_u32(&tmem_empty_bar[as]), 0);  // accumulator stage drained (leader's barrier)
     }
+    if (warp == 4 && lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -688,9 +791,31 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, 
 }
 
 
+// output tensor map for the coalesced epilogue (bf16 NHWC, or its pixel-shuffle view [B, H, 2(dy), W, 2(dx)*Cq])
+int make_out_map(CUtensorMap* m, const ConvParams& p, void* out) {
+  if (p.out_mode == 1) {
+    const uint64_t Cq = (uint64_t)p.Cout / 4, Ho = 2ull * p.H, Wo = 2ull * p.W;
+    const uint64_t dims[5] = {2 * Cq, (uint64_t)p.W, 2ull, (uint64_t)p.H, (uint64_t)p.B};
+    const uint64_t str[4] = {2 * Cq * 2, Wo * Cq * 2, 2 * Wo * Cq * 2, Ho * Wo * Cq * 2};
+    const uint32_t box[5] = {(uint32_t)EPI_COLS, (uint32_t)p.TW, 1u, (uint32_t)p.TH, (uint32_t)p.TB};
+    return encode_map(m, out, 5, dims, str, box);
+  }
+  const uint64_t C = (uint64_t)p.Cout;
+  const uint64_t dims[5] = {C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B, 1ull};
+  const uint64_t str[4] = {C * 2, (uint64_t)p.W * C * 2, (uint64_t)p.H * p.W * C * 2, (uint64_t)p.B * p.H * p.W * C * 2};
+  const uint32_t box[5] = {(uint32_t)EPI_COLS, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB, 1u};
+  return encode_map(m, out, 5, dims, str, box);
+}
+
 template <int BN, int STAGES>
 int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 2 * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
+  CUtensorMap mo = ma;
+  if (!p.out_f32) {
+    int rc = make_out_map(&mo, p, p.out);
+    if (rc) return rc;
+  }
   static bool configured = false;
   static std::mutex mu;
   {
@@ -705,7 +830,7 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
   int clusters = kd_num_sms() / 2;
   if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_pair_kernel<BN, STAGES><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, p, (int)pair_tiles);
+  conv_gemm_pair_kernel<BN, STAGES><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, p, (int)pair_tiles);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
