@@ -330,7 +330,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 //                arrive; all four TMA loads of a stage complete_tx on the leader's barrier (.cta_group::2 loads).
 //   empty[s]     both CTAs, count 1: tcgen05.commit multicast from the leader's MMA thread.
 //   tmem_full[a] both CTAs, count 1: commit multicast after the last k-block of a tile.
-//   tmem_empty[a] leader only, count 8: one elected lane of each of the 4 epilogue warps of both CTAs (remote arrive).
+//   tmem_empty[a] leader only, count 16: one elected lane of each of the 8 epilogue warps of both CTAs (remote arrive).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -402,11 +402,11 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+__device__ __forceinline__ void epi_barrier(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }  // 4 warps of one set
 
-constexpr int NUM_THREADS2 = 256;
+constexpr int NUM_THREADS2 = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7 and 8-11: two epilogue sets
 constexpr int EPI_COLS = 64;                          // columns per staged group = one 128-byte swizzle row of bf16
-constexpr int EPI_STAGE_BYTES = BM * EPI_COLS * 2;    // 16 KB per staging buffer, two buffers
+constexpr int EPI_STAGE_BYTES = BM * EPI_COLS * 2;    // 16 KB staging buffer per epilogue set (two sets)
 
 // epilogue of one 32-column chunk of one accumulator row (shared by both kernels' store paths)
 __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const uint32_t* acc, int nc, int b, int h, int w) {
@@ -506,7 +506,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 8);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 16);  // 8 epilogue warps x 2 CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -583,12 +583,16 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue (both CTAs): own 128 rows x BN columns
+    // two sets of 4 warps (one warp of each set per SM sub-partition): set 0 takes the even 64-column groups, set 1 the odd
     const int quarter = warp & 3;
+    const int set = (warp - 4) >> 2;
+    const bool issuer = (quarter == 0) && (lane == 0);  // this set's TMA-store thread
+    const uint32_t stage = epi_smem + set * EPI_STAGE_BYTES;
     const int r = quarter * 32 + lane;
     const int tw = r % p.TW;
     const int th = (r / p.TW) % p.TH;
     const int tb = r / (p.TW * p.TH);
-    uint32_t tile_iter = 0, epi_it = 0;
+    uint32_t tile_iter = 0;
     for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
       const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
       const int n_tile = t % p.n_tiles;
@@ -606,7 +610,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (p.out_f32) {
         // fp32 output (tests / small tensors): direct per-row stores
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        for (int chunk = set; chunk < BN / 32; chunk += 2) {
           uint32_t acc[32];
           tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
           tmem_ld_wait();
@@ -618,13 +622,28 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const bool tile_in_range = tile_b < p.tiles_b;
         const int Cq = p.Cout >> 2;
 #pragma unroll 1
-        for (int g = 0; g < BN / EPI_COLS; ++g, ++epi_it) {
+        for (int g = set; g < BN / EPI_COLS; g += 2) {
           const int nc0 = n0 + g * EPI_COLS;
-          if (nc0 >= p.Cout) break;  // uniform across the CTA
-          const uint32_t stage = epi_smem + (epi_it & 1) * EPI_STAGE_BYTES;
-          // the TMA store that last read this staging buffer (two groups ago) must have finished reading it
-          if (warp == 4 && lane == 0) tma_store_wait_read<1>();
-          epi_barrier();
+          if (nc0 >= p.Cout) break;  // uniform across the set
+          // prefetch this row's 64 addend values (8 x 16 B) before any waiting: their latency hides behind the barrier
+          // and the TMEM load
+          int4 addv[8];
+          const bool has_add = (p.addend != nullptr) && row_ok && !p.addend_f32;
+          if (has_add) {
+            long long off;
+            if (p.out_mode == 1) {
+              const int q4 = nc0 / Cq, c = nc0 - q4 * Cq;
+              off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
+            } else {
+              off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc0;
+            }
+            const int4* ap = reinterpret_cast<const int4*>(reinterpret_cast<const bf16*>(p.addend) + off);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) addv[q] = (nc0 + q * 8 + 8 <= p.Cout) ? ld_stream(ap + q) : make_int4(0, 0, 0, 0);
+          }
+          // the TMA store that last read this set's staging buffer must have finished reading it
+          if (issuer) tma_store_wait_read<0>();
+          epi_barrier(set);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t acc[32];
@@ -661,8 +680,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                   float4 a0 = ap[0], a1 = ap[1];
                   a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
                 } else {
-                  bf16x8 raw = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.addend) + add_off + q * 8);
-                  bf16x8_to_float(raw, a);
+                  bf16x8_to_float(*reinterpret_cast<const bf16x8*>(&addv[half * 4 + q]), a);
                 }
                 if (gate != nullptr) {
                   const float4 g0 = *reinterpret_cast<const float4*>(gate + q * 8);
@@ -680,8 +698,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
           }
           fence_proxy_async_smem();
-          epi_barrier();
-          if (warp == 4 && lane == 0) {
+          epi_barrier(set);
+          if (issuer) {
             if (tile_in_range) {
               if (p.out_mode == 1) {
                 const int q4 = nc0 / Cq, c0 = nc0 - q4 * Cq;
@@ -698,7 +716,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_remote_arrive(smem_u32(&tmem_empty_bar[as]), 0);  // accumulator stage drained (leader's barrier)
     }
-    if (warp == 4 && lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk stores
+    if (issuer) tma_store_wait_read<0>();  // staging smem must outlive the last bulk stores
   }
 
   tc_fence_before();
