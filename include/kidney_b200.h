@@ -20,7 +20,7 @@
  *    synchronisation; every call is CUDA-graph capturable.
  *  - return 0 on success, negative KdStatus otherwise; message via
  *    kd_last_error() (thread-local).
- *  - activations inside the UNet are NHWC bf16 ("[B,H,W,C]"), image state at the
+ *  - activations inside the UNet are NHWC fp16 ("[B,H,W,C]"), image state at the
  *    sampler level is NCHW fp32 exactly as in the reference.
  */
 #ifndef KIDNEY_B200_H_
@@ -58,7 +58,7 @@ int kd_check_device(void);
  *           image tokens (Attention/CrossAttention to_q,to_kv,to_out, ChanFeedForward).
  * out[b,h,w,n] = act( sum_{tap,c} A[b, h+dy(tap), w+dx(tap), c] * Wt[n, tap, c] + bias[n] )
  *                + addend_scale[b,n] * addend[b,h,w,n]
- * A is the channel concatenation of two NHWC bf16 sources (xa: Ca channels, xb: Cb channels; Cb may be 0).
+ * A is the channel concatenation of two NHWC fp16 sources (xa: Ca channels, xb: Cb channels; Cb may be 0).
  */
 typedef struct KdConvDesc {
   int mode;         /* 0: ksize x ksize, stride 1, zero pad ksize/2.  1: 2x2 stride-2 "pixel-unshuffle" taps (Downsample);
@@ -69,7 +69,7 @@ typedef struct KdConvDesc {
   int ksize;        /* 1 or 3 for mode 0; ignored otherwise */
   int act;          /* KdAct applied before the addend */
   int out_mode;     /* 0: NHWC [B,H,W,Cout].  1: pixel-shuffle(2): weight rows ordered (dy,dx,c) -> out [B,2H,2W,Cout/4] */
-  int out_f32;      /* 0: bf16 output, 1: fp32 output */
+  int out_f32;      /* 0: fp16 output, 1: fp32 output */
   int addend_f32;   /* dtype of addend (same layout as out) */
 } KdConvDesc;
 
@@ -78,7 +78,7 @@ typedef struct KdConvDesc {
 int kd_set_conv_impl(int impl);
 
 int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
-                 const void* w /* bf16 [Cout, taps*(Ca+Cb)], K ordered (tap, channel) */, const float* bias /* [Cout] or NULL */,
+                 const void* w /* fp16 [Cout, taps*(Ca+Cb)], K ordered (tap, channel) */, const float* bias /* [Cout] or NULL */,
                  const void* addend /* or NULL */, const float* addend_scale /* [B,Cout] or NULL (=1) */, void* out,
                  kd_stream_t stream);
 
@@ -97,12 +97,12 @@ int kd_sinu_emb(const float* t, const float* weights, int B, int half, float* ou
  *           cat(x, skip * 2^-0.5) of the up path (two sources, the second pre-scaled by src_scale).
  * kd_gn_stats writes deterministic per-block partial sums  partial[b][blk][g] = {sum, sumsq} over the channels of this
  * source that fall into global group g (global channel = c_offset + c; group = global channel / group_size). */
-int kd_gn_stats(const void* x /* bf16 [B,HW,C] */, int B, long HW, int C, int c_offset, int group_size, int num_groups,
+int kd_gn_stats(const void* x /* fp16 [B,HW,C] */, int B, long HW, int C, int c_offset, int group_size, int num_groups,
                 float* partial /* [B][nblk][num_groups][2] */, int nblk, kd_stream_t stream);
 int kd_gn_finalize(const float* partial_a, int nblk_a, float scale_a, const float* partial_b, int nblk_b, float scale_b, int B,
                    int num_groups, double count /* elements per (b, group) */, float eps, float* mean_rstd /* [B][G][2] */,
                    kd_stream_t stream);
-/* y = act( ((x*src_scale - mean) * rstd * gamma + beta) * (scale + 1) + shift ), bf16 out.
+/* y = act( ((x*src_scale - mean) * rstd * gamma + beta) * (scale + 1) + shift ), fp16 out.
  * scale_shift: fp32 rows of 2*Ctot values laid out as time_mlp output (scale = first Ctot, shift = last Ctot), row b at
  * scale_shift + b*ss_stride (so one launch of kd_linear_small can produce every block's time_mlp at once), or NULL. */
 int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int group_size, int num_groups, float src_scale,
@@ -111,37 +111,37 @@ int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int
 
 /* ------------------------------------------------------------------ K4: GlobalContext gate
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */
-int kd_rowdot(const void* x /* bf16 [B,HW,C] */, const float* w /* [C] */, const float* bias /* [1] or NULL */, float* out /* [B,HW] */,
+int kd_rowdot(const void* x /* fp16 [B,HW,C] */, const float* w /* [C] */, const float* bias /* [1] or NULL */, float* out /* [B,HW] */,
               int B, long HW, int C, kd_stream_t stream);
 int kd_gca_pool(const void* x, const float* logits, int B, long HW, int C, int nblk, float* part /* [B][nblk][C] */,
                 float* ml /* [B][nblk][2] = {max, sumexp} */, kd_stream_t stream);
 int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled /* [B][C] */, kd_stream_t stream);
-/* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); bf16 in/out */
+/* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); fp16 in/out */
 int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, int B, long HW, int C, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ LayerNorm over channels of NHWC tokens
  * replaces: imagen-pytorch LayerNorm / ChanLayerNorm (gain only, eps 1e-5) and nn.LayerNorm (gain + bias).
  * y = (x - mean) * rsqrt(var + eps) * g (+ bias) (+ residual) */
-int kd_layernorm_bf16(const void* x, const float* g, const float* bias, const void* residual, void* y, long M, int C, float eps,
+int kd_layernorm_h16(const void* x, const float* g, const float* bias, const void* residual, void* y, long M, int C, float eps,
                       kd_stream_t stream);
 int kd_layernorm_f32(const float* x, const float* g, const float* bias, float* y, long M, int C, float eps, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ K5: attention
  * replaces: Attention.forward (multi-query: one shared 64-d K/V head, null k/v and optional context k/v prepended) and
  *           CrossAttention.forward (full multi-head K/V from <= 64 conditioning tokens + null k/v). */
-int kd_kv_assemble(const void* qkv /* bf16 [B,N,ld] */, long ld, int kv_col, const float* ctx_kv /* [B,Jc,128] or NULL */, int Jc,
-                   const float* null_kv /* [2,64] */, void* kv_out /* bf16 [B, Jc+1+N, 128] */, int B, int N, kd_stream_t stream);
-int kd_attn_mqa(const void* q /* bf16 [B,N,*] */, long ldq, const void* kv /* bf16 [B,J,128] */, void* out /* bf16 [B,N,heads*64] */,
+int kd_kv_assemble(const void* qkv /* fp16 [B,N,ld] */, long ld, int kv_col, const float* ctx_kv /* [B,Jc,128] or NULL */, int Jc,
+                   const float* null_kv /* [2,64] */, void* kv_out /* fp16 [B, Jc+1+N, 128] */, int B, int N, kd_stream_t stream);
+int kd_attn_mqa(const void* q /* fp16 [B,N,*] */, long ldq, const void* kv /* fp16 [B,J,128] */, void* out /* fp16 [B,N,heads*64] */,
                 int B, int N, int J, int heads, float scale, kd_stream_t stream);
 int kd_attn_cross(const void* q, long ldq, const float* kv /* [B,Jc,2*heads*64] */, const float* null_kv /* [2,64] */,
-                  void* out /* bf16 [B,N,heads*64] */, int B, int N, int Jc, int heads, float scale, kd_stream_t stream);
+                  void* out /* fp16 [B,N,heads*64] */, int B, int N, int Jc, int heads, float scale, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ init / final convolutions
  * replaces: CrossEmbedLayer (3 convs k=3,7,15 concatenated) via an im2col panel consumed by kd_conv_gemm mode 2,
  *           and Unet.final_conv (3x3, Cout = 3) on cat(x, lowres_cond_img). */
-int kd_im2col_nchw(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int W, int ksize, void* out /* bf16 [B*H*W, Kp] */,
+int kd_im2col_nchw(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int W, int ksize, void* out /* fp16 [B*H*W, Kp] */,
                    int Kp, kd_stream_t stream);
-int kd_final_conv(const void* xa /* bf16 [B,H,W,Ca] */, int Ca, const float* xb /* fp32 NCHW [B,Cb,H,W] or NULL */, int Cb,
+int kd_final_conv(const void* xa /* fp16 [B,H,W,Ca] */, int Ca, const float* xb /* fp32 NCHW [B,Cb,H,W] or NULL */, int Cb,
                   const float* w /* fp32 [Cout][3][3][Ca+Cb] */, const float* bias, float* out /* fp32 NCHW [B,Cout,H,W] */, int B,
                   int H, int W, int Cout, kd_stream_t stream);
 

@@ -45,7 +45,7 @@ SIGNATURES = {
     "kd_gca_pool": (c_int, [_P, _P, _I, _L, _I, _I, _P, _P, _P]),
     "kd_gca_finalize": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "kd_gate_residual": (c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
-    "kd_layernorm_bf16": (c_int, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "kd_layernorm_h16": (c_int, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_layernorm_f32": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_kv_assemble": (c_int, [_P, _L, _I, _P, _I, _P, _P, _I, _I, _P]),
     "kd_attn_mqa": (c_int, [_P, _L, _P, _P, _I, _I, _I, _I, _F, _P]),

@@ -70,48 +70,48 @@ __global__ void sinu_emb_kernel(const float* __restrict__ t, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ K/V assembly for MQA
-// kv_out[b] = [ ctx rows (Jc) | null row | token rows (N) ], each row = 64 k values then 64 v values (bf16)
-__global__ void kv_assemble_kernel(const bf16* __restrict__ qkv, long ld, int kv_col, const float* __restrict__ ctx_kv, int Jc,
-                                   const float* __restrict__ null_kv, bf16* __restrict__ kv_out, int N) {
+// kv_out[b] = [ ctx rows (Jc) | null row | token rows (N) ], each row = 64 k values then 64 v values (h16)
+__global__ void kv_assemble_kernel(const h16* __restrict__ qkv, long ld, int kv_col, const float* __restrict__ ctx_kv, int Jc,
+                                   const float* __restrict__ null_kv, h16* __restrict__ kv_out, int N) {
   const int b = blockIdx.y;
   const int J = Jc + 1 + N;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, 8-col group): 16 groups per row
   if (idx >= (long)J * 16) return;
   const int row = (int)(idx >> 4), g = (int)(idx & 15);
-  bf16* dst = kv_out + ((long)b * J + row) * 128 + g * 8;
+  h16* dst = kv_out + ((long)b * J + row) * 128 + g * 8;
   if (row < Jc) {
     const float* src = ctx_kv + ((long)b * Jc + row) * 128 + g * 8;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = src[j];
-    *reinterpret_cast<bf16x8*>(dst) = float_to_bf16x8(v);
+    *reinterpret_cast<h16x8*>(dst) = float_to_h16x8(v);
   } else if (row == Jc) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = null_kv[g * 8 + j];  // [2,64] row-major = k(64) then v(64)
-    *reinterpret_cast<bf16x8*>(dst) = float_to_bf16x8(v);
+    *reinterpret_cast<h16x8*>(dst) = float_to_h16x8(v);
   } else {
-    const bf16* src = qkv + ((long)b * N + (row - Jc - 1)) * ld + kv_col + g * 8;
+    const h16* src = qkv + ((long)b * N + (row - Jc - 1)) * ld + kv_col + g * 8;
     *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(src);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ MQA flash attention
 // One CTA = 64 queries of one (b, head); 4 warps x 16 query rows; keys processed in tiles of 64 with online softmax.
-// Tensor cores via mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  K/V tiles ([64 keys][64] k and v) staged in smem.
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, const uint32_t* b) {
+// Tensor cores via mma.sync.m16n8k16 (h16 in, fp32 accumulate).  K/V tiles ([64 keys][64] k and v) staged in smem.
+__device__ __forceinline__ void mma_f16_16816(float* c, const uint32_t* a, const uint32_t* b) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-constexpr int AT_BQ = 64, AT_BK = 64, AT_D = 64, AT_PAD = 8;  // smem row = 72 bf16 (144 B) to avoid bank conflicts
+constexpr int AT_BQ = 64, AT_BK = 64, AT_D = 64, AT_PAD = 8;  // smem row = 72 h16 (144 B) to avoid bank conflicts
 
-__global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ kv,
-                                                       bf16* __restrict__ out, int N, int J, int heads, float scale_log2) {
-  __shared__ __align__(16) bf16 sK[AT_BK][AT_D + AT_PAD];
-  __shared__ __align__(16) bf16 sV[AT_BK][AT_D + AT_PAD];
+__global__ void __launch_bounds__(128) attn_mqa_kernel(const h16* __restrict__ q, long ldq, const h16* __restrict__ kv,
+                                                       h16* __restrict__ out, int N, int J, int heads, float scale_log2) {
+  __shared__ __align__(16) h16 sK[AT_BK][AT_D + AT_PAD];
+  __shared__ __align__(16) h16 sV[AT_BK][AT_D + AT_PAD];
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * AT_BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;  // mma fragment coordinates
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ 
 
   // Q fragments (A operand, 16 x 64 per warp): 4 k-steps x 4 regs, loaded straight from global
   uint32_t qa[4][4];
-  const bf16* qb = q + (long)b * N * ldq + head * AT_D;
+  const h16* qb = q + (long)b * N * ldq + head * AT_D;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     const int c = ks * 16 + tig * 2;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ 
     for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-  const bf16* kvb = kv + (long)b * J * 128;
+  const h16* kvb = kv + (long)b * J * 128;
   for (int j0 = 0; j0 < J; j0 += AT_BK) {
     __syncthreads();
     // stage K and V tiles: 64 rows x (8 + 8) 16-byte vectors
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ 
         // B (col-major k x n): element (k, n) = K[n][k]; thread holds k = ks*16 + tig*2 (+1), (+8,+9) for n = nt*8 + gid
         bfrag[0] = *reinterpret_cast<const uint32_t*>(&sK[nt * 8 + gid][ks * 16 + tig * 2]);
         bfrag[1] = *reinterpret_cast<const uint32_t*>(&sK[nt * 8 + gid][ks * 16 + tig * 2 + 8]);
-        mma_bf16_16816(s_acc[nt], qa[ks], bfrag);
+        mma_f16_16816(s_acc[nt], qa[ks], bfrag);
       }
     }
     // online softmax (rows gid and gid+8); logits scaled into log2 domain
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ 
       }
       // accumulator layout (row gid: cols 2*tig,2*tig+1 ; row gid+8: same) maps onto the A fragment of k-step nt/2
       const int ks = nt >> 1, hi = nt & 1;
-      pa[ks][hi * 2 + 0] = pack_bf16x2(pv[0], pv[1]);
-      pa[ks][hi * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+      pa[ks][hi * 2 + 0] = pack_h16x2(pv[0], pv[1]);
+      pa[ks][hi * 2 + 1] = pack_h16x2(pv[2], pv[3]);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -222,14 +222,14 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ 
         const int k0 = ks * 16 + tig * 2;
         const int n = nt * 8 + gid;
         uint32_t bfrag[2];
-        bf162 t0, t1;
+        h162 t0, t1;
         t0.x = sV[k0][n];
         t0.y = sV[k0 + 1][n];
         t1.x = sV[k0 + 8][n];
         t1.y = sV[k0 + 9][n];
         bfrag[0] = *reinterpret_cast<uint32_t*>(&t0);
         bfrag[1] = *reinterpret_cast<uint32_t*>(&t1);
-        mma_bf16_16816(o_acc[nt], pa[ks], bfrag);
+        mma_f16_16816(o_acc[nt], pa[ks], bfrag);
       }
     }
   }
@@ -240,20 +240,20 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const bf16* __restrict__ 
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
   }
   const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-  bf16* ob = out + (long)b * N * heads * AT_D + head * AT_D;
+  h16* ob = out + (long)b * N * heads * AT_D + head * AT_D;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const int c = nt * 8 + tig * 2;
-    if (row_a < N) *reinterpret_cast<uint32_t*>(ob + (long)row_a * heads * AT_D + c) = pack_bf16x2(o_acc[nt][0] * inv0, o_acc[nt][1] * inv0);
+    if (row_a < N) *reinterpret_cast<uint32_t*>(ob + (long)row_a * heads * AT_D + c) = pack_h16x2(o_acc[nt][0] * inv0, o_acc[nt][1] * inv0);
     if (row_a + 8 < N)
-      *reinterpret_cast<uint32_t*>(ob + (long)(row_a + 8) * heads * AT_D + c) = pack_bf16x2(o_acc[nt][2] * inv1, o_acc[nt][3] * inv1);
+      *reinterpret_cast<uint32_t*>(ob + (long)(row_a + 8) * heads * AT_D + c) = pack_h16x2(o_acc[nt][2] * inv1, o_acc[nt][3] * inv1);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ cross attention, J <= 64
 // warp = one head, lane = one token; K/V of all heads staged in smem as fp32 pairs -> broadcast reads.
-__global__ void __launch_bounds__(256) attn_cross_kernel(const bf16* __restrict__ q, long ldq, const float* __restrict__ kv,
-                                                         const float* __restrict__ null_kv, bf16* __restrict__ out, int N, int Jc,
+__global__ void __launch_bounds__(256) attn_cross_kernel(const h16* __restrict__ q, long ldq, const float* __restrict__ kv,
+                                                         const float* __restrict__ null_kv, h16* __restrict__ out, int N, int Jc,
                                                          int heads, float scale) {
   extern __shared__ float skv[];  // [J][heads][2][64]
   const int b = blockIdx.y;
@@ -275,11 +275,11 @@ __global__ void __launch_bounds__(256) attn_cross_kernel(const bf16* __restrict_
   const int n = blockIdx.x * tokens_per_block + tsub * 32 + lane;
   if (n >= N) return;
   float qv[64];
-  const bf16* qp = q + ((long)b * N + n) * ldq + h * 64;
+  const h16* qp = q + ((long)b * N + n) * ldq + h * 64;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     int4 raw = *reinterpret_cast<const int4*>(qp + g * 8);
-    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), qv + g * 8);
+    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), qv + g * 8);
   }
   float m = -INFINITY, l = 0.f;
   float acc[64];
@@ -300,13 +300,13 @@ __global__ void __launch_bounds__(256) attn_cross_kernel(const bf16* __restrict_
     m = mn;
   }
   const float inv = 1.f / l;
-  bf16* op = out + ((long)b * N + n) * HD + h * 64;
+  h16* op = out + ((long)b * N + n) * HD + h * 64;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = acc[g * 8 + j] * inv;
-    *reinterpret_cast<bf16x8*>(op + g * 8) = float_to_bf16x8(v);
+    *reinterpret_cast<h16x8*>(op + g * 8) = float_to_h16x8(v);
   }
 }
 
@@ -339,7 +339,7 @@ extern "C" int kd_kv_assemble(const void* qkv, long ld, int kv_col, const float*
   KD_REQUIRE(ld % 8 == 0 && kv_col % 8 == 0, "kd_kv_assemble: ld / kv_col must be multiples of 8");
   const long total = (long)(Jc + 1 + N) * 16;
   kv_assemble_kernel<<<dim3((unsigned)((total + 255) / 256), B), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(qkv), ld, kv_col, ctx_kv, Jc, null_kv, reinterpret_cast<bf16*>(kv_out), N);
+      reinterpret_cast<const h16*>(qkv), ld, kv_col, ctx_kv, Jc, null_kv, reinterpret_cast<h16*>(kv_out), N);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -350,8 +350,8 @@ extern "C" int kd_attn_mqa(const void* q, long ldq, const void* kv, void* out, i
   KD_REQUIRE(q && kv && out && B > 0 && N > 0 && J > 0 && heads > 0, "kd_attn_mqa: bad argument");
   KD_REQUIRE(ldq % 8 == 0, "kd_attn_mqa: ldq must be a multiple of 8");
   dim3 grid(kd_ceil_div(N, AT_BQ), heads, B);
-  attn_mqa_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(kv),
-                                            reinterpret_cast<bf16*>(out), N, J, heads, scale * 1.4426950408889634f);
+  attn_mqa_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const h16*>(q), ldq, reinterpret_cast<const h16*>(kv),
+                                            reinterpret_cast<h16*>(out), N, J, heads, scale * 1.4426950408889634f);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -371,7 +371,7 @@ extern "C" int kd_attn_cross(const void* q, long ldq, const float* kv, const flo
   }
   const int tokens_per_block = 32 * (8 / heads);
   dim3 grid(kd_ceil_div(N, tokens_per_block), B);
-  attn_cross_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(q), ldq, kv, null_kv, reinterpret_cast<bf16*>(out), N,
+  attn_cross_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const h16*>(q), ldq, kv, null_kv, reinterpret_cast<h16*>(out), N,
                                                  Jc, heads, scale);
   KD_LAUNCH_CHECK();
   return KD_OK;

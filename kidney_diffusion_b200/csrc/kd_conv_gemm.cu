@@ -1,7 +1,7 @@
 // K1: implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA).
 //
 //   M = B*H*W output pixels (tile = TB x TH x TW = 128 pixels), N = Cout, K = taps * (Ca + Cb).
-//   A operand: for k-block (tap, 64-channel chunk) one TMA tiled load of a [TB,TH,TW,64] box of the NHWC bf16
+//   A operand: for k-block (tap, 64-channel chunk) one TMA tiled load of a [TB,TH,TW,64] box of the NHWC h16
 //              activation tensor, shifted by the tap offset; out-of-bounds coordinates are zero-filled by the TMA unit,
 //              which implements the convolution's zero padding.  The box lands in shared memory as 128 rows x 128 B with
 //              the 128-byte swizzle, i.e. exactly the canonical K-major SWIZZLE_128B UMMA operand layout.
@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int BK = 64;  // 64 h16 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
 
@@ -88,8 +88,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one CTA
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, h16 x h16 -> fp32, one CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -138,8 +138,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  // instruction descriptor: D = fp32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // instruction descriptor: D = fp32 (bit 4), A = B = h16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -231,7 +231,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot once these MMAs have read it
       }
@@ -287,8 +287,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             float4 a0 = ap[0], a1 = ap[1];
             a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
           } else {
-            bf16x8 raw = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.addend) + add_off + g * 8);
-            bf16x8_to_float(raw, a);
+            h16x8 raw = *reinterpret_cast<const h16x8*>(reinterpret_cast<const h16*>(p.addend) + add_off + g * 8);
+            h16x8_to_float(raw, a);
           }
           if (gate != nullptr) {
             const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
@@ -303,7 +303,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           op[0] = make_float4(v[0], v[1], v[2], v[3]);
           op[1] = make_float4(v[4], v[5], v[6], v[7]);
         } else {
-          *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.out) + out_off + g * 8) = float_to_bf16x8(v);
+          *reinterpret_cast<h16x8*>(reinterpret_cast<h16*>(p.out) + out_off + g * 8) = float_to_h16x8(v);
         }
       }
     }
@@ -373,7 +373,7 @@ __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -405,7 +405,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void epi_barrier(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }  // 4 warps of one set
 
 constexpr int NUM_THREADS2 = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7 and 8-11: two epilogue sets
-constexpr int EPI_COLS = 64;                          // columns per staged group = one 128-byte swizzle row of bf16
+constexpr int EPI_COLS = 64;                          // columns per staged group = one 128-byte swizzle row of h16
 constexpr int EPI_STAGE_BYTES = BM * EPI_COLS * 2;    // 16 KB staging buffer per epilogue set (two sets)
 
 // epilogue of one 32-column chunk of one accumulator row (shared by both kernels' store paths)
@@ -441,8 +441,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
         float4 a0 = ap[0], a1 = ap[1];
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
       } else {
-        bf16x8 raw = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.addend) + out_off + g * 8);
-        bf16x8_to_float(raw, a);
+        h16x8 raw = *reinterpret_cast<const h16x8*>(reinterpret_cast<const h16*>(p.addend) + out_off + g * 8);
+        h16x8_to_float(raw, a);
       }
       if (gate != nullptr) {
         const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
@@ -457,7 +457,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
       op[0] = make_float4(v[0], v[1], v[2], v[3]);
       op[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-      *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.out) + out_off + g * 8) = float_to_bf16x8(v);
+      *reinterpret_cast<h16x8*>(reinterpret_cast<h16*>(p.out) + out_off + g * 8) = float_to_h16x8(v);
     }
   }
 }
@@ -470,8 +470,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
-  // instruction descriptor: D fp32, A = B = bf16, K-major, N = BN, M = 256 (pair)
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  // instruction descriptor: D fp32, A = B = h16, K-major, N = BN, M = 256 (pair)
+  constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -575,7 +575,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint64_t b_desc = make_sw128_desc(a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(smem_u32(&empty_bar[s]));
         }
         umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
@@ -618,7 +618,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
         }
       } else {
-        // bf16 output: 64-column groups staged in 128B-swizzled smem and written with one coalesced TMA store each
+        // h16 output: 64-column groups staged in 128B-swizzled smem and written with one coalesced TMA store each
         const bool tile_in_range = tile_b < p.tiles_b;
         const int Cq = p.Cout >> 2;
 #pragma unroll 1
@@ -637,7 +637,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             } else {
               off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc0;
             }
-            const int4* ap = reinterpret_cast<const int4*>(reinterpret_cast<const bf16*>(p.addend) + off);
+            const int4* ap = reinterpret_cast<const int4*>(reinterpret_cast<const h16*>(p.addend) + off);
 #pragma unroll
             for (int q = 0; q < 8; ++q) addv[q] = (nc0 + q * 8 + 8 <= p.Cout) ? ld_stream(ap + q) : make_int4(0, 0, 0, 0);
           }
@@ -680,7 +680,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                   float4 a0 = ap[0], a1 = ap[1];
                   a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
                 } else {
-                  bf16x8_to_float(*reinterpret_cast<const bf16x8*>(&addv[half * 4 + q]), a);
+                  h16x8_to_float(*reinterpret_cast<const h16x8*>(&addv[half * 4 + q]), a);
                 }
                 if (gate != nullptr) {
                   const float4 g0 = *reinterpret_cast<const float4*>(gate + q * 8);
@@ -692,7 +692,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               }
               const uint32_t chunk16 = (uint32_t)(half * 4 + q);
               const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
-              const bf16x8 o8 = float_to_bf16x8(v);
+              const h16x8 o8 = float_to_h16x8(v);
               const int4 ov = *reinterpret_cast<const int4*>(&o8);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z), "r"(ov.w) : "memory");
             }
@@ -761,7 +761,7 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
     if (gstr[i] % 16 != 0) KD_FAIL(KD_ERR_BAD_ARG, "TMA stride %d = %llu not a multiple of 16 bytes", i, (unsigned long long)gstr[i]);
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) KD_FAIL(KD_ERR_BAD_ARG, "TMA base pointer not 16-byte aligned");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) KD_FAIL(KD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -809,7 +809,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, 
 }
 
 
-// output tensor map for the coalesced epilogue (bf16 NHWC, or its pixel-shuffle view [B, H, 2(dy), W, 2(dx)*Cq])
+// output tensor map for the coalesced epilogue (h16 NHWC, or its pixel-shuffle view [B, H, 2(dy), W, 2(dx)*Cq])
 int make_out_map(CUtensorMap* m, const ConvParams& p, void* out) {
   if (p.out_mode == 1) {
     const uint64_t Cq = (uint64_t)p.Cout / 4, Ho = 2ull * p.H, Wo = 2ull * p.W;

@@ -1,15 +1,15 @@
 // The two "edge" convolutions of the UNet whose shapes are not tensor-core friendly on their own:
 //   * CrossEmbedLayer input convs (Cin = 3..10 image channels, kernels 3/7/15): an im2col panel builder (NCHW fp32 ->
-//     [pixels, Kp] bf16) feeding kd_conv_gemm mode 2, where the three kernels are merged into one 15x15 weight matrix.
+//     [pixels, Kp] h16) feeding kd_conv_gemm mode 2, where the three kernels are merged into one 15x15 weight matrix.
 //   * final_conv (3x3, Cout = 3) on cat(x, lowres_cond_img): HBM-bound, a shared-memory tiled SIMT kernel that also
-//     converts NHWC bf16 -> NCHW fp32.
+//     converts NHWC h16 -> NCHW fp32.
 #include "kd_common.cuh"
 
 namespace {
 
 constexpr int IC_TW = 64;  // pixels of one image row per block
 
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, int C, int H, int W, int ks, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, int C, int H, int W, int ks, h16* __restrict__ out,
                                                      int Kp) {
   extern __shared__ float sm[];
   const int pad = ks >> 1;
@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
       const int off = lut[g * 8 + j];
       v[j] = off >= 0 ? tile[off + px] : 0.f;
     }
-    bf16x8 o8 = float_to_bf16x8(v);
-    bf16* dst = out + (((long)b * H + h) * W + w0 + px) * Kp + g * 8;
+    h16x8 o8 = float_to_h16x8(v);
+    h16* dst = out + (((long)b * H + h) * W + w0 + px) * Kp + g * 8;
     st_stream(dst, *reinterpret_cast<int4*>(&o8));
   }
 }
@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------------ final conv
 constexpr int FC_TH = 8, FC_TW = 32, FC_CH = 32;           // 256 pixels per block, 32-channel chunks
 constexpr int FC_HH = FC_TH + 2, FC_HW = FC_TW + 2;         // halo tile
-constexpr int FC_PIX_STRIDE = FC_CH + 8;                    // bf16 elements per halo pixel (80 B: conflict-free 16 B reads)
+constexpr int FC_PIX_STRIDE = FC_CH + 8;                    // h16 elements per halo pixel (80 B: conflict-free 16 B reads)
 constexpr int FC_MAXCO = 4;
 
-__global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb,
+__global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ out, int H, int W, int Cout) {
-  __shared__ __align__(16) bf16 s_act[FC_HH * FC_HW * FC_PIX_STRIDE];
+  __shared__ __align__(16) h16 s_act[FC_HH * FC_HW * FC_PIX_STRIDE];
   __shared__ __align__(16) float s_w[FC_MAXCO * 9 * FC_CH];
   __shared__ float s_xb[4 * FC_HH * FC_HW];
   const int Ctot = Ca + Cb;
@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict_
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int py = ty + tap / 3, px = tx + tap % 3;
-      const bf16* ap = &s_act[(py * FC_HW + px) * FC_PIX_STRIDE];
+      const h16* ap = &s_act[(py * FC_HW + px) * FC_PIX_STRIDE];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         float a[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(ap + v * 8), a);
+        h16x8_to_float(*reinterpret_cast<const h16x8*>(ap + v * 8), a);
 #pragma unroll
         for (int co = 0; co < FC_MAXCO; ++co) {
           if (co < Cout) {
@@ -153,7 +153,7 @@ extern "C" int kd_im2col_nchw(const float* x, int B, int C, int H, int W, int ks
   }
   KD_REQUIRE(H <= 65535 && B <= 65535, "kd_im2col_nchw: H / B exceed grid limits");
   dim3 grid(kd_ceil_div(W, IC_TW), H, B);
-  im2col_kernel<<<grid, 256, smem, stream>>>(x, C, H, W, ksize, reinterpret_cast<bf16*>(out), Kp);
+  im2col_kernel<<<grid, 256, smem, stream>>>(x, C, H, W, ksize, reinterpret_cast<h16*>(out), Kp);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -167,7 +167,7 @@ extern "C" int kd_final_conv(const void* xa, int Ca, const float* xb, int Cb, co
   KD_REQUIRE(Cout >= 1 && Cout <= FC_MAXCO, "kd_final_conv: Cout must be <= %d", FC_MAXCO);
   KD_REQUIRE(kd_ceil_div(H, FC_TH) <= 65535 && B <= 65535, "kd_final_conv: grid too large");
   dim3 grid(kd_ceil_div(W, FC_TW), kd_ceil_div(H, FC_TH), B);
-  final_conv_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(xa), Ca, xb, Cb, w, bias, out, H, W, Cout);
+  final_conv_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const h16*>(xa), Ca, xb, Cb, w, bias, out, H, W, Cout);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

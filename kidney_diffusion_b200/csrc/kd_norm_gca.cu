@@ -1,4 +1,4 @@
-// HBM-bound NHWC bf16 kernels around the convolutions: GroupNorm (stats / finalize / apply), GlobalContext pooling,
+// HBM-bound NHWC h16 kernels around the convolutions: GroupNorm (stats / finalize / apply), GlobalContext pooling,
 // gate * h + residual, LayerNorm over channels.  All reductions are fixed-order (no float atomics) so results are
 // identical run to run and across GPU counts.
 //
@@ -12,7 +12,7 @@ namespace {
 __host__ __device__ inline int threads_for_oct(int oct) { return oct >= 256 ? 256 : (256 / oct) * oct; }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, long HW, int C, int c_offset, int group_size, int G,
+__global__ void gn_stats_kernel(const h16* __restrict__ x, long HW, int C, int c_offset, int group_size, int G,
                                 float* __restrict__ partial, int nblk) {
   extern __shared__ float sm[];  // [T][2]
   const int oct = C >> 3;
@@ -24,12 +24,12 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long HW, int C, int 
   const long per = (HW + nblk - 1) / nblk;
   const long p0 = (long)blockIdx.x * per;
   const long p1 = p0 + per < HW ? p0 + per : HW;
-  const bf16* xb = x + (long)b * HW * C + (long)o * 8;
+  const h16* xb = x + (long)b * HW * C + (long)o * 8;
   float s = 0.f, ss = 0.f;
   for (long p = p0 + pl; p < p1; p += lanes) {
     int4 raw = ld_stream(xb + p * C);
     float v[8];
-    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s += v[j];
@@ -90,7 +90,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ pa, int nblk_a, flo
   }
 }
 
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long HW, int C, int c_offset, int group_size,
+__global__ void gn_apply_kernel(const h16* __restrict__ x, h16* __restrict__ y, long HW, int C, int c_offset, int group_size,
                                 int G, float src_scale, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ scale_shift, long ss_stride, int Ctot,
                                 int act, int nblk) {
@@ -120,22 +120,22 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
   const long per = (HW + nblk - 1) / nblk;
   const long p0 = (long)blockIdx.x * per;
   const long p1 = p0 + per < HW ? p0 + per : HW;
-  const bf16* xb = x + (long)b * HW * C + (long)o * 8;
-  bf16* yb = y + (long)b * HW * C + (long)o * 8;
+  const h16* xb = x + (long)b * HW * C + (long)o * 8;
+  h16* yb = y + (long)b * HW * C + (long)o * 8;
   for (long p = p0 + pl; p < p1; p += lanes) {
     int4 raw = ld_stream(xb + p * C);
     float v[8];
-    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(A[j], v[j], Bc[j]), act);
-    bf16x8 o8 = float_to_bf16x8(v);
+    h16x8 o8 = float_to_h16x8(v);
     *reinterpret_cast<int4*>(yb + p * C) = *reinterpret_cast<int4*>(&o8);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ GlobalContext
 // logits[b, n] = sum_c x[b,n,c] * w[c] + bias : one warp per pixel (two pixels per warp when C = 128).
-__global__ void rowdot_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void rowdot_kernel(const h16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                               float* __restrict__ out, long rows, int C) {
   const int oct = C >> 3;
   const int sub = (oct < 32 && (oct & (oct - 1)) == 0) ? oct : 32;  // lanes cooperating on one pixel (power of two)
@@ -152,7 +152,7 @@ __global__ void rowdot_kernel(const bf16* __restrict__ x, const float* __restric
       for (int o = sl; o < oct; o += sub) {
         int4 raw = ld_stream(x + r * C + o * 8);
         float v[8];
-        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+        h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
         const float4 w0 = *reinterpret_cast<const float4*>(w + o * 8);
         const float4 w1 = *reinterpret_cast<const float4*>(w + o * 8 + 4);
         acc += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
@@ -164,7 +164,7 @@ __global__ void rowdot_kernel(const bf16* __restrict__ x, const float* __restric
 }
 
 // Softmax-weighted channel pooling, one block per (pixel chunk, b): partial[b][blk][c] = sum_n exp(l_n - m_blk) x[n,c]
-__global__ void gca_pool_kernel(const bf16* __restrict__ x, const float* __restrict__ logits, long HW, int C, int nblk,
+__global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restrict__ logits, long HW, int C, int nblk,
                                 float* __restrict__ part, float* __restrict__ ml) {
   extern __shared__ float sm[];  // max(T, lanes*C) floats
   __shared__ float s_red[32];
@@ -194,12 +194,12 @@ __global__ void gca_pool_kernel(const bf16* __restrict__ x, const float* __restr
   m = s_m;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float l = 0.f;
-  const bf16* xb = x + (long)b * HW * C + (long)o * 8;
+  const h16* xb = x + (long)b * HW * C + (long)o * 8;
   for (long p = p0 + pl; p < p1; p += lanes) {
     const float e = __expf(lg[p] - m);
     int4 raw = ld_stream(xb + p * C);
     float v[8];
-    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(e, v[j], acc[j]);
     l += e;
@@ -279,8 +279,8 @@ __global__ void gca_finalize_kernel(const float* __restrict__ part, const float*
   pooled[(long)b * C + c] = ((s0 + s1) + (s2 + s3)) / s_L;
 }
 
-__global__ void gate_residual_kernel(const bf16* __restrict__ h, const float* __restrict__ gate, const bf16* __restrict__ res,
-                                     bf16* __restrict__ out, long HW, int C, int nblk) {
+__global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __restrict__ gate, const h16* __restrict__ res,
+                                     h16* __restrict__ out, long HW, int C, int nblk) {
   const int oct = C >> 3;
   const int lanes = blockDim.x / oct;
   const int o = threadIdx.x % oct;
@@ -296,18 +296,18 @@ __global__ void gate_residual_kernel(const bf16* __restrict__ h, const float* __
   for (long p = p0 + pl; p < p1; p += lanes) {
     int4 raw = ld_stream(h + base + p * C);
     float v[8];
-    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
     if (res != nullptr) {
       int4 rr = ld_stream(res + base + p * C);
       float r[8];
-      bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rr), r);
+      h16x8_to_float(*reinterpret_cast<h16x8*>(&rr), r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], g[j], r[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= g[j];
     }
-    bf16x8 o8 = float_to_bf16x8(v);
+    h16x8 o8 = float_to_h16x8(v);
     *reinterpret_cast<int4*>(out + base + p * C) = *reinterpret_cast<int4*>(&o8);
   }
 }
@@ -328,11 +328,11 @@ __global__ void layernorm_kernel(const void* __restrict__ x_, const float* __res
       ss += v * v;
     }
   } else {
-    const bf16* x = reinterpret_cast<const bf16*>(x_) + row * C;
+    const h16* x = reinterpret_cast<const h16*>(x_) + row * C;
     for (int o = lane; o < (C >> 3); o += 32) {
       int4 raw = *reinterpret_cast<const int4*>(x + o * 8);
       float v[8];
-      bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+      h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s += v[j];
@@ -355,13 +355,13 @@ __global__ void layernorm_kernel(const void* __restrict__ x_, const float* __res
       y[c] = v;
     }
   } else {
-    const bf16* x = reinterpret_cast<const bf16*>(x_) + row * C;
-    const bf16* res = reinterpret_cast<const bf16*>(res_);
-    bf16* y = reinterpret_cast<bf16*>(y_) + row * C;
+    const h16* x = reinterpret_cast<const h16*>(x_) + row * C;
+    const h16* res = reinterpret_cast<const h16*>(res_);
+    h16* y = reinterpret_cast<h16*>(y_) + row * C;
     for (int o = lane; o < (C >> 3); o += 32) {
       int4 raw = *reinterpret_cast<const int4*>(x + o * 8);
       float v[8];
-      bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), v);
+      h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[j] = (v[j] - mean) * rstd * g[o * 8 + j];
@@ -370,11 +370,11 @@ __global__ void layernorm_kernel(const void* __restrict__ x_, const float* __res
       if (res) {
         int4 rr = *reinterpret_cast<const int4*>(res + row * C + o * 8);
         float r[8];
-        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rr), r);
+        h16x8_to_float(*reinterpret_cast<h16x8*>(&rr), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += r[j];
       }
-      bf16x8 o8 = float_to_bf16x8(v);
+      h16x8 o8 = float_to_h16x8(v);
       *reinterpret_cast<int4*>(y + o * 8) = *reinterpret_cast<int4*>(&o8);
     }
   }
@@ -402,7 +402,7 @@ extern "C" int kd_gn_stats(const void* x, int B, long HW, int C, int c_offset, i
   KD_CHECK_OCT(C);
   KD_REQUIRE(group_size % 8 == 0 && c_offset % 8 == 0 && num_groups <= 32, "kd_gn_stats: group_size/c_offset must be multiples of 8");
   const int T = threads_for_oct(C / 8);
-  gn_stats_kernel<<<dim3(nblk, B), T, T * 2 * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(x), HW, C, c_offset,
+  gn_stats_kernel<<<dim3(nblk, B), T, T * 2 * sizeof(float), stream>>>(reinterpret_cast<const h16*>(x), HW, C, c_offset,
                                                                         group_size, num_groups, partial, nblk);
   KD_LAUNCH_CHECK();
   return KD_OK;
@@ -426,7 +426,7 @@ extern "C" int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_
   KD_REQUIRE(group_size % 8 == 0 && c_offset % 8 == 0, "kd_gn_apply: group_size/c_offset must be multiples of 8");
   const int T = threads_for_oct(C / 8);
   const int nblk = pick_nblk(HW, T / (C / 8), B);
-  gn_apply_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), HW, C, c_offset,
+  gn_apply_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), HW, C, c_offset,
                                                    group_size, num_groups, src_scale, mean_rstd, gamma, beta, scale_shift, ss_stride,
                                                    Ctot, act, nblk);
   KD_LAUNCH_CHECK();
@@ -444,7 +444,7 @@ extern "C" int kd_rowdot(const void* x, const float* w, const float* bias, float
   const long cap = (long)kd_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  rowdot_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), w, bias, out, rows, C);
+  rowdot_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const h16*>(x), w, bias, out, rows, C);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -456,7 +456,7 @@ extern "C" int kd_gca_pool(const void* x, const float* logits, int B, long HW, i
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
   const size_t smem = sizeof(float) * (size_t)T * 8;
-  gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const bf16*>(x), logits, HW, C, nblk, part, ml);
+  gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const h16*>(x), logits, HW, C, nblk, part, ml);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -477,16 +477,16 @@ extern "C" int kd_gate_residual(const void* h, const float* gate, const void* re
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
   const int nblk = pick_nblk(HW, T / (C / 8), B);
-  gate_residual_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const bf16*>(h), gate, reinterpret_cast<const bf16*>(res),
-                                                        reinterpret_cast<bf16*>(out), HW, C, nblk);
+  gate_residual_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const h16*>(h), gate, reinterpret_cast<const h16*>(res),
+                                                        reinterpret_cast<h16*>(out), HW, C, nblk);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
 
-extern "C" int kd_layernorm_bf16(const void* x, const float* g, const float* bias, const void* residual, void* y, long M, int C,
+extern "C" int kd_layernorm_h16(const void* x, const float* g, const float* bias, const void* residual, void* y, long M, int C,
                                  float eps, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(x && g && y && M > 0 && C > 0 && C % 8 == 0, "kd_layernorm_bf16: bad argument (C=%d)", C);
+  KD_REQUIRE(x && g && y && M > 0 && C > 0 && C % 8 == 0, "kd_layernorm_h16: bad argument (C=%d)", C);
   layernorm_kernel<false><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(x, g, bias, residual, y, M, C, eps);
   KD_LAUNCH_CHECK();
   return KD_OK;

@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import KdConvDesc, check
 
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+ACT_DTYPE = torch.float16  # 16-bit activation / weight dtype of the CUDA path (kd_common.cuh: h16), fp32 accumulation
 PRED = {"noise": 0, "v": 1, "x_start": 2}
 
 launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -77,13 +78,13 @@ def set_conv_impl(impl):
 
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
               addend=None, addend_scale=None, out=None):
-    """xa / xb: NHWC bf16 [B,H,W,C]; w: packed bf16 [Cout, taps*(Ca+Cb)]; returns NHWC (bf16 or fp32)."""
-    _chk(xa, torch.bfloat16, "xa")
-    _chk(w, torch.bfloat16, "w")
+    """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32)."""
+    _chk(xa, ACT_DTYPE, "xa")
+    _chk(w, ACT_DTYPE, "w")
     B, Hin, Win, Ca = xa.shape
     Cb = 0
     if xb is not None:
-        _chk(xb, torch.bfloat16, "xb")
+        _chk(xb, ACT_DTYPE, "xb")
         assert xb.shape[:3] == xa.shape[:3]
         Cb = xb.shape[3]
     H, W = (Hin // 2, Win // 2) if mode == 1 else (Hin, Win)
@@ -92,7 +93,7 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
     assert w.shape[1] == taps * (Ca + Cb), f"weight K {w.shape[1]} != {taps}*({Ca}+{Cb})"
     if out is None:
         oshape = (B, 2 * H, 2 * W, Cout // 4) if out_mode == 1 else (B, H, W, Cout)
-        out = torch.empty(oshape, device=xa.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+        out = torch.empty(oshape, device=xa.device, dtype=torch.float32 if out_f32 else ACT_DTYPE)
     addend_f32 = 0
     if addend is not None:
         assert addend.is_contiguous() and addend.shape == out.shape
@@ -112,13 +113,13 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
 
 def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=None, algo_k=None):
     """Plain GEMM y[M,N] = act(x[M,K] @ w[N,K]^T + bias) + addend on tensor cores (mode 2)."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(w, torch.bfloat16, "w")
+    _chk(x, ACT_DTYPE, "x")
+    _chk(w, ACT_DTYPE, "w")
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K
     if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else ACT_DTYPE)
     else:
         assert out.is_contiguous() and out.shape == (M, N)
         out_f32 = out.dtype == torch.float32
@@ -179,7 +180,7 @@ def _nblk(HW, C, B):
 
 
 def gn_stats(x, c_offset, group_size, num_groups):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     B, H, W, C = x.shape
     HW = H * W
     nblk = _nblk(HW, C, B)
@@ -201,7 +202,7 @@ def gn_finalize(partial_a, scale_a, partial_b, scale_b, count, eps=1e-5):
 
 def gn_apply(x, mean_rstd, gamma, beta, *, c_offset, group_size, num_groups, src_scale=1.0, scale_shift=None, ctot=None,
              act=ACT_SILU):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     B, H, W, C = x.shape
     y = torch.empty_like(x)
     ctot = ctot if ctot is not None else C
@@ -218,7 +219,7 @@ def gn_apply(x, mean_rstd, gamma, beta, *, c_offset, group_size, num_groups, src
 
 # ------------------------------------------------------------------------------------------------ GlobalContext
 def rowdot(x, w, bias):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     B, H, W, C = x.shape
     out = torch.empty((B, H * W), device=x.device, dtype=torch.float32)
     check(lib().kd_rowdot(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), B, H * W, C, _stream()), "kd_rowdot")
@@ -240,7 +241,7 @@ def gca_pool(x, logits):
 
 
 def gate_residual(h, gate, res):
-    _chk(h, torch.bfloat16, "h")
+    _chk(h, ACT_DTYPE, "h")
     B, H, W, C = h.shape
     out = torch.empty_like(h)
     check(lib().kd_gate_residual(_ptr(h), _ptr(gate), _ptr(res), _ptr(out), B, H * W, C, _stream()), "kd_gate_residual")
@@ -249,12 +250,12 @@ def gate_residual(h, gate, res):
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
-def layernorm_bf16(x, g, bias=None, residual=None, eps=1e-5):
-    _chk(x, torch.bfloat16, "x")
+def layernorm_h16(x, g, bias=None, residual=None, eps=1e-5):
+    _chk(x, ACT_DTYPE, "x")
     C = x.shape[-1]
     M = x.numel() // C
     y = torch.empty_like(x)
-    check(lib().kd_layernorm_bf16(_ptr(x), _ptr(g), _ptr(bias), _ptr(residual), _ptr(y), M, C, eps, _stream()), "kd_layernorm_bf16")
+    check(lib().kd_layernorm_h16(_ptr(x), _ptr(g), _ptr(bias), _ptr(residual), _ptr(y), M, C, eps, _stream()), "kd_layernorm_h16")
     _count()
     return y
 
@@ -271,30 +272,30 @@ def layernorm_f32(x, g, bias=None, eps=1e-5):
 
 # ------------------------------------------------------------------------------------------------ attention
 def kv_assemble(qkv, kv_col, ctx_kv, null_kv):
-    """qkv: bf16 [B,N,ld]; ctx_kv: fp32 [B,Jc,128] or None; null_kv fp32 [2,64] -> bf16 [B, Jc+1+N, 128]."""
+    """qkv: fp16 [B,N,ld]; ctx_kv: fp32 [B,Jc,128] or None; null_kv fp32 [2,64] -> fp16 [B, Jc+1+N, 128]."""
     B, N, ld = qkv.shape
     Jc = 0 if ctx_kv is None else ctx_kv.shape[1]
-    out = torch.empty((B, Jc + 1 + N, 128), device=qkv.device, dtype=torch.bfloat16)
+    out = torch.empty((B, Jc + 1 + N, 128), device=qkv.device, dtype=ACT_DTYPE)
     check(lib().kd_kv_assemble(_ptr(qkv), ld, kv_col, _ptr(ctx_kv), Jc, _ptr(null_kv), _ptr(out), B, N, _stream()), "kd_kv_assemble")
     _count()
     return out
 
 
 def attn_mqa(q, kv, heads, scale):
-    """q: bf16 [B,N,ld] (first heads*64 columns are the queries); kv: bf16 [B,J,128]."""
+    """q: fp16 [B,N,ld] (first heads*64 columns are the queries); kv: fp16 [B,J,128]."""
     B, N, ld = q.shape
     J = kv.shape[1]
-    out = torch.empty((B, N, heads * 64), device=q.device, dtype=torch.bfloat16)
+    out = torch.empty((B, N, heads * 64), device=q.device, dtype=ACT_DTYPE)
     check(lib().kd_attn_mqa(_ptr(q), ld, _ptr(kv), _ptr(out), B, N, J, heads, scale, _stream()), "kd_attn_mqa")
     _count()
     return out
 
 
 def attn_cross(q, kv, null_kv, heads, scale):
-    """q: bf16 [B,N,heads*64]; kv: fp32 [B,Jc,2*heads*64]; null_kv fp32 [2,64]."""
+    """q: fp16 [B,N,heads*64]; kv: fp32 [B,Jc,2*heads*64]; null_kv fp32 [2,64]."""
     B, N, ld = q.shape
     Jc = kv.shape[1]
-    out = torch.empty((B, N, heads * 64), device=q.device, dtype=torch.bfloat16)
+    out = torch.empty((B, N, heads * 64), device=q.device, dtype=ACT_DTYPE)
     check(lib().kd_attn_cross(_ptr(q), ld, _ptr(kv), _ptr(null_kv), _ptr(out), B, N, Jc, heads, scale, _stream()), "kd_attn_cross")
     _count()
     return out
@@ -304,15 +305,15 @@ def attn_cross(q, kv, null_kv, heads, scale):
 def im2col_nchw(x, ksize, Kp):
     _chk(x, torch.float32, "x")
     B, C, H, W = x.shape
-    out = torch.empty((B * H * W, Kp), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((B * H * W, Kp), device=x.device, dtype=ACT_DTYPE)
     check(lib().kd_im2col_nchw(_ptr(x), B, C, H, W, ksize, _ptr(out), Kp, _stream()), "kd_im2col_nchw")
     _count()
     return out
 
 
 def final_conv(xa, xb, w, bias):
-    """xa: NHWC bf16; xb: NCHW fp32 or None; w: fp32 [Cout,3,3,Ca+Cb] -> NCHW fp32 [B,Cout,H,W]."""
-    _chk(xa, torch.bfloat16, "xa")
+    """xa: NHWC fp16; xb: NCHW fp32 or None; w: fp32 [Cout,3,3,Ca+Cb] -> NCHW fp32 [B,Cout,H,W]."""
+    _chk(xa, ACT_DTYPE, "xa")
     B, H, W, Ca = xa.shape
     Cb = 0 if xb is None else xb.shape[1]
     Cout = w.shape[0]

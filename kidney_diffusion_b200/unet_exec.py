@@ -3,7 +3,7 @@
 Everything that touches activations is a hand-written kernel reached through ``ops`` (C ABI).  torch is used for
 memory, for one-time weight packing, and for the x-independent nearest resize of the conditioning images.
 
-Data layout in HBM: activations NHWC bf16; "raw" tensors (conv outputs / residual stream) and "act" tensors
+Data layout in HBM: activations NHWC fp16; "raw" tensors (conv outputs / residual stream) and "act" tensors
 (GroupNorm+SiLU applied, the A operand of the next conv) are both bf16; statistics, softmax, time / conditioning towers
 and the GlobalContext gate are fp32.  Weights are packed once: conv [Cout, kh*kw*Cin] bf16 K-major (tap-major,
 channel-minor) so a (tap, 64-channel chunk) k-block is one TMA box.
@@ -26,7 +26,7 @@ from torch import nn
 from . import ops
 from .modules import Parallel, PixelShuffleUpsample, TransformerBlock, exists
 
-BF16 = torch.bfloat16
+BF16 = ops.ACT_DTYPE  # 16-bit activation / weight dtype (fp16)
 IM2COL_BUDGET_BYTES = 4 << 30
 
 
@@ -301,12 +301,12 @@ class UnetExecutor:
     def _cross_attn(self, P, h, c):
         B, H, W, C = h.shape
         J = c.shape[1]
-        xn = ops.layernorm_bf16(h, P["norm_g"])
+        xn = ops.layernorm_h16(h, P["norm_g"])
         q = ops.conv_gemm(xn, P["wq"], None, ksize=1)
         kv = ops.linear_small(c.view(B * J, -1), P["wkv"]).view(B, J, -1)
         o = ops.attn_cross(q.view(B, H * W, -1), kv, P["null_kv"], P["heads"], P["scale"])
         o = ops.conv_gemm(o.view(B, H, W, -1), P["wo"], None, ksize=1)
-        return ops.layernorm_bf16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
+        return ops.layernorm_h16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
 
     def _resnet(self, P, xa, xb, ss_all, c):
         B = xa.shape[0]
@@ -335,7 +335,7 @@ class UnetExecutor:
         B, H, W, C = x.shape
         N = H * W
         for L in P.layers:
-            xn = ops.layernorm_bf16(x, L["norm_g"])
+            xn = ops.layernorm_h16(x, L["norm_g"])
             qkv = ops.conv_gemm(xn, L["wqkv"], None, ksize=1).view(B, N, -1)
             ctx_kv = None
             if exists(c) and exists(L["ctx"]):
@@ -345,10 +345,10 @@ class UnetExecutor:
             kv = ops.kv_assemble(qkv, L["heads"] * 64, ctx_kv, L["null_kv"])
             o = ops.attn_mqa(qkv, kv, L["heads"], L["scale"])
             o = ops.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
-            x = ops.layernorm_bf16(o, L["out_g"], residual=x)
-            f = ops.layernorm_bf16(x, L["ff_g0"])
+            x = ops.layernorm_h16(o, L["out_g"], residual=x)
+            f = ops.layernorm_h16(x, L["ff_g0"])
             f = ops.conv_gemm(f, L["ff_w1"], None, ksize=1, act=ops.ACT_GELU)
-            f = ops.layernorm_bf16(f, L["ff_g1"])
+            f = ops.layernorm_h16(f, L["ff_g1"])
             x = ops.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
         return x
 

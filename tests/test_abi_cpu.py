@@ -55,7 +55,7 @@ def test_product_path_fails_loudly_without_gpu():
     with pytest.raises(RuntimeError):
         im.sample(batch_size=1, use_tqdm=False)
     with pytest.raises(_lib.KdError):
-        ops.conv_gemm(torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16), torch.zeros(64, 576, dtype=torch.bfloat16))
+        ops.conv_gemm(torch.zeros(1, 8, 8, 64, dtype=torch.float16), torch.zeros(64, 576, dtype=torch.float16))
 
 
 def test_no_product_module_imports_the_oracle():

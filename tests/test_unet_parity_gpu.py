@@ -26,7 +26,7 @@ def _report(taps_dev, taps_ref):
     ("u3_b1_rect", U3_KW, True, 64, 1),
 ])
 def test_unet_forward_parity(cuda_lib, name, kw, lowres, S, B):
-    ou, pu = make_pair(kw, lowres_cond=lowres, seed=hash(name) % 1000)
+    ou, pu = make_pair(kw, lowres_cond=lowres, seed=sum(map(ord, name)))
     g = torch.Generator().manual_seed(5)
     x = torch.randn(B, 3, S, S, generator=g)
     t = torch.tensor([2.18, -0.5, 5.0])[:B]
@@ -130,9 +130,14 @@ def test_sample_parity_sr_stage_with_inpainting(cuda_lib, use_graph):
     assert worst < TOL and err < TOL
 
 
+CFG1_KW = dict(dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=3, layer_attns=(False, True, True, True),
+               layer_cross_attns=(False, True, True, True))
+
+
 def test_sample_parity_base_stage(cuda_lib):
-    """Config-1 shaped run: unconditional base unet, eps objective, 6 steps, batch 4."""
-    oi, pi = _imagen_pair([U1_KW], (32,), (6,), ("noise",))
+    """BASELINE config 1: unconditional 64x64 base UNet, dim = 128 (shape of train_uncond.py:30-37), eps objective, batch 4;
+    8 of the sampling steps so the fp32 CPU oracle stays within ~10 s."""
+    oi, pi = _imagen_pair([CFG1_KW], (64,), (8,), ("noise",))
     kn = KeyedNoise(7)
     ref_steps, dev_steps = [], []
     ref = oi.sample(batch_size=4, noise_fn=kn.cpu, step_taps=ref_steps)
