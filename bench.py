@@ -261,7 +261,7 @@ def run_b200(args):
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_per_step, higher_is_better=True,
-            scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
             config=dict(workload="cfg3 ultra-res SR UNet 256->1024 (train_ultra_res_v_param.py:51-60) v-param patch-step, random init",
                         global_batch=world * B, per_gpu_batch=B, patch=S, parallelism=f"patch-parallel x{world} (no collective)",
                         l2="inputs larger than L2 (activations >= 0.27 GB per tensor per patch)", state_dtype="f32",

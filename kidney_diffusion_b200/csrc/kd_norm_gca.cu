@@ -26,7 +26,24 @@ __global__ void gn_stats_kernel(const h16* __restrict__ x, long HW, int C, int c
   const long p1 = p0 + per < HW ? p0 + per : HW;
   const h16* xb = x + (long)b * HW * C + (long)o * 8;
   float s = 0.f, ss = 0.f;
-  for (long p = p0 + pl; p < p1; p += lanes) {
+  long p = p0 + pl;
+  // 4 independent 16-byte loads in flight per thread (the kernel is pure streaming: latency hiding is all that matters)
+  for (; p + 3L * lanes < p1; p += 4L * lanes) {
+    int4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = ld_stream(xb + (p + (long)u * lanes) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      h16x8_to_float(*reinterpret_cast<h16x8*>(&raw[u]), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += v[j];
+        ss += v[j] * v[j];
+      }
+    }
+  }
+  for (; p < p1; p += lanes) {
     int4 raw = ld_stream(xb + p * C);
     float v[8];
     h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
@@ -122,7 +139,22 @@ __global__ void gn_apply_kernel(const h16* __restrict__ x, h16* __restrict__ y, 
   const long p1 = p0 + per < HW ? p0 + per : HW;
   const h16* xb = x + (long)b * HW * C + (long)o * 8;
   h16* yb = y + (long)b * HW * C + (long)o * 8;
-  for (long p = p0 + pl; p < p1; p += lanes) {
+  long p = p0 + pl;
+  for (; p + 3L * lanes < p1; p += 4L * lanes) {
+    int4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = ld_stream(xb + (p + (long)u * lanes) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      h16x8_to_float(*reinterpret_cast<h16x8*>(&raw[u]), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(A[j], v[j], Bc[j]), act);
+      h16x8 o8 = float_to_h16x8(v);
+      *reinterpret_cast<int4*>(yb + (p + (long)u * lanes) * C) = *reinterpret_cast<int4*>(&o8);
+    }
+  }
+  for (; p < p1; p += lanes) {
     int4 raw = ld_stream(xb + p * C);
     float v[8];
     h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
@@ -226,14 +258,17 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
   }
 }
 
-// block = 256 channels of one batch element: the per-chunk rescale factors exp(m_k - M) are computed once into smem
+// block = 64 channels x 4 k-slices of one batch element: the per-chunk rescale factors exp(m_k - M) are computed once
+// into smem, each thread sums a fixed quarter of the chunks (fixed order), then the 4 slices are added in fixed order
 __global__ void gca_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ml, int nblk, int C,
                                     float* __restrict__ pooled) {
-  extern __shared__ float f[];  // [nblk]
+  extern __shared__ float f[];  // [nblk] + [4][64]
   __shared__ float s_red[8];
   __shared__ float s_M, s_L;
+  float* s_part = f + nblk;
   const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cl = threadIdx.x & 63, ks = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* mlb = ml + (long)b * nblk * 2;
   float m = -INFINITY;
@@ -265,18 +300,21 @@ __global__ void gca_finalize_kernel(const float* __restrict__ part, const float*
     s_L = ll;
   }
   __syncthreads();
-  if (c >= C) return;
-  const float* pp = part + (long)b * nblk * C + c;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= nblk; k += 4) {
-    s0 = fmaf(f[k], pp[(long)k * C], s0);
-    s1 = fmaf(f[k + 1], pp[(long)(k + 1) * C], s1);
-    s2 = fmaf(f[k + 2], pp[(long)(k + 2) * C], s2);
-    s3 = fmaf(f[k + 3], pp[(long)(k + 3) * C], s3);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const float* pp = part + (long)b * nblk * C + c;
+    const int per = (nblk + 3) / 4;
+    const int k0 = ks * per, k1 = (k0 + per < nblk) ? k0 + per : nblk;
+    int k = k0;
+    for (; k + 2 <= k1; k += 2) {
+      s0 = fmaf(f[k], pp[(long)k * C], s0);
+      s1 = fmaf(f[k + 1], pp[(long)(k + 1) * C], s1);
+    }
+    for (; k < k1; ++k) s0 = fmaf(f[k], pp[(long)k * C], s0);
   }
-  for (; k < nblk; ++k) s0 = fmaf(f[k], pp[(long)k * C], s0);
-  pooled[(long)b * C + c] = ((s0 + s1) + (s2 + s3)) / s_L;
+  s_part[ks * 64 + cl] = s0 + s1;
+  __syncthreads();
+  if (ks == 0 && c < C) pooled[(long)b * C + c] = ((s_part[cl] + s_part[64 + cl]) + (s_part[128 + cl] + s_part[192 + cl])) / s_L;
 }
 
 __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __restrict__ gate, const h16* __restrict__ res,
@@ -465,7 +503,7 @@ extern "C" int kd_gca_finalize(const float* part, const float* ml, int B, int nb
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(part && ml && pooled && B > 0 && nblk > 0 && C > 0, "kd_gca_finalize: bad argument");
   KD_REQUIRE(nblk <= 8192, "kd_gca_finalize: nblk too large");
-  gca_finalize_kernel<<<dim3(kd_ceil_div(C, 256), B), 256, nblk * sizeof(float), stream>>>(part, ml, nblk, C, pooled);
+  gca_finalize_kernel<<<dim3(kd_ceil_div(C, 64), B), 256, (nblk + 256) * sizeof(float), stream>>>(part, ml, nblk, C, pooled);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -175,7 +175,7 @@ def _nblk(HW, C, B):
     lanes = max(1, threads // oct_)
     # independent of the batch size on purpose: a sample's reduction order (hence its bits) must not depend on which
     # other patches share its batch (patch-grid invariance across GPU counts)
-    want = 148 * 2
+    want = 148 * 4
     return int(max(1, min(want, -(-HW // lanes))))
 
 
