@@ -85,7 +85,7 @@ int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
 /* ------------------------------------------------------------------ small-M linear (time / conditioning towers, GCA MLP)
  * replaces: nn.Linear on (B, features) tensors: to_time_hiddens, to_time_cond, to_time_tokens, ResnetBlock.time_mlp,
  *           GlobalContext.net, CrossAttention.to_kv on the conditioning tokens.
- * y[m, n] = post_act( sum_k pre_act(x[m,k]) * w[n,k] + bias[n] ), fp32 everywhere, M <= 4096 rows. */
+ * y[m, n] = post_act( sum_k pre_act(x[m,k]) * w[n,k] + bias[n] ), fp32 everywhere, M <= 65536 rows (meant for M of a few hundred at most). */
 int kd_linear_small(const float* x, int M, int K, long ldx, const float* w, const float* bias, float* y, int N, long ldy,
                     int pre_act, int post_act, kd_stream_t stream);
 
@@ -135,6 +135,13 @@ int kd_attn_mqa(const void* q /* fp16 [B,N,*] */, long ldq, const void* kv /* fp
                 int B, int N, int J, int heads, float scale, kd_stream_t stream);
 int kd_attn_cross(const void* q, long ldq, const float* kv /* [B,Jc,2*heads*64] */, const float* null_kv /* [2,64] */,
                   void* out /* fp16 [B,N,heads*64] */, int B, int N, int Jc, int heads, float scale, kd_stream_t stream);
+
+/* replaces: PerceiverAttention of the text-conditioning tower (Unet.attn_pool; train.py models only): fp32 multi-head
+ *           attention of Nq latent queries over J keys, q [B,Nq,heads*64], kv [B,J,2*heads*64] (k | v), once per sample(). */
+int kd_attn_small_f32(const float* q, const float* kv, float* out, int B, int Nq, int J, int heads, float scale, kd_stream_t stream);
+/* out = a*x + b*y (fp32): residual adds of the conditioning towers and classifier-free guidance
+ * (Unet.forward_with_cond_scale: null + (cond - null) * scale = scale*cond + (1-scale)*null). */
+int kd_axpby(const float* x, const float* y, float a, float b, float* out, long n, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ init / final convolutions
  * replaces: CrossEmbedLayer (3 convs k=3,7,15 concatenated) via an im2col panel consumed by kd_conv_gemm mode 2,

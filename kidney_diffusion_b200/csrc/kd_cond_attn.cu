@@ -310,12 +310,62 @@ __global__ void __launch_bounds__(256) attn_cross_kernel(const h16* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ small fp32 attention
+// PerceiverResampler attention of the text-conditioning tower (36 latent queries x <= 512 keys, once per sample() call):
+// one warp per (b, head, query); lanes stride over the keys with a private online softmax, merged by shuffles.
+__global__ void __launch_bounds__(128) attn_small_f32_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                             float* __restrict__ out, int Nq, int J, int heads, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int HD = heads * 64;
+  const int b = blockIdx.z;
+  const long local = wid;
+  if (local >= (long)Nq * heads) return;
+  const int h = (int)(local % heads), n = (int)(local / heads);
+  const float* qp = q + ((long)b * Nq + n) * HD + h * 64;
+  float qv[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) qv[d] = qp[d] * scale;
+  float m = -INFINITY, l = 0.f, acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+  for (int j = lane; j < J; j += 32) {
+    const float* kp = kv + ((long)b * J + j) * 2 * HD + h * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s = fmaf(qv[d], kp[d], s);
+    const float mn = fmaxf(m, s);
+    const float corr = __expf(m - mn), pj = __expf(s - mn);
+    l = l * corr + pj;
+    const float* vp = kp + HD;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) acc[d] = fmaf(pj, vp[d], acc[d] * corr);
+    m = mn;
+  }
+  // merge the 32 lanes' partial softmaxes
+  const float M = warp_max(m);
+  const float f = (m == -INFINITY) ? 0.f : __expf(m - M);
+  const float L = warp_sum(l * f);
+  float* op = out + ((long)b * Nq + n) * HD + h * 64;
+#pragma unroll
+  for (int d = 0; d < 64; ++d) {
+    const float v = warp_sum(acc[d] * f);
+    if (lane == (d & 31)) op[d] = v / L;
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b, float* __restrict__ out, long n) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a * x[i] + b * y[i];
+}
+
 }  // namespace
 
 extern "C" int kd_linear_small(const float* x, int M, int K, long ldx, const float* w, const float* bias, float* y, int N, long ldy,
                                int pre_act, int post_act, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(x && w && y && M > 0 && K > 0 && N > 0 && M <= 4096, "kd_linear_small: bad argument (M=%d K=%d N=%d)", M, K, N);
+  KD_REQUIRE(x && w && y && M > 0 && K > 0 && N > 0 && M <= 65536, "kd_linear_small: bad argument (M=%d K=%d N=%d)", M, K, N);
   const int row_groups = kd_ceil_div(M, 8) < 64 ? kd_ceil_div(M, 8) : 64;
   dim3 grid(kd_ceil_div(N, 8), row_groups);
   linear_small_kernel<8><<<grid, 256, 0, stream>>>(x, M, K, ldx, w, bias, y, N, ldy, pre_act, post_act);
@@ -373,6 +423,27 @@ extern "C" int kd_attn_cross(const void* q, long ldq, const float* kv, const flo
   dim3 grid(kd_ceil_div(N, tokens_per_block), B);
   attn_cross_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const h16*>(q), ldq, kv, null_kv, reinterpret_cast<h16*>(out), N,
                                                  Jc, heads, scale);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_attn_small_f32(const float* q, const float* kv, float* out, int B, int Nq, int J, int heads, float scale,
+                                 kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(q && kv && out && B > 0 && Nq > 0 && J > 0 && heads > 0, "kd_attn_small_f32: bad argument");
+  const long warps = (long)Nq * heads;
+  dim3 grid((unsigned)((warps + 3) / 4), 1, B);
+  attn_small_f32_kernel<<<grid, 128, 0, stream>>>(q, kv, out, Nq, J, heads, scale);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_axpby(const float* x, const float* y, float a, float b, float* out, long n, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && y && out && n > 0, "kd_axpby: bad argument");
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  axpby_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, a, b, out, n);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -68,7 +68,8 @@ class CounterNoise:
 class _StepGraph:
     """One UNet forward for fixed (B, S) captured as a CUDA graph (~800 kernel launches per step otherwise)."""
 
-    def __init__(self, ex, B, S, channels, lowres_t, device):
+    def __init__(self, ex, B, S, channels, lowres_t, device, drop=0.0):
+        self.drop = drop
         self.x = torch.zeros((B, channels, S, S), device=device, dtype=torch.float32)
         self.time = torch.zeros((B,), device=device, dtype=torch.float32)
         self.lowres_t = lowres_t.clone() if lowres_t is not None else None
@@ -77,12 +78,12 @@ class _StepGraph:
         stream.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(stream):
             for _ in range(2):  # warm-up: function attributes, allocator pools
-                ex.forward(self.x, self.time, self.lowres_t)
+                ex.forward(self.x, self.time, self.lowres_t, drop=drop)
         torch.cuda.current_stream(device).wait_stream(stream)
         before = ops.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.pred = ex.forward(self.x, self.time, self.lowres_t)
+            self.pred = ex.forward(self.x, self.time, self.lowres_t, drop=drop)
         self.launches = ops.launch_count - before
 
     def __call__(self, img, time_row, lowres_t):
@@ -101,8 +102,9 @@ class StageRun:
 
     def __init__(self, imagen, unet_number, shape, *, noise, lowres_cond_img, lowres_noise_level, text_embeds, text_mask, cond_images,
                  inpaint_images, inpaint_masks, inpaint_resample_times, cond_scale):
-        if cond_scale != 1.0:
-            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is row N4 of the scope table, not built yet")
+        assert not (cond_scale != 1.0 and not imagen.can_classifier_guidance), (
+            "imagen was not trained with conditional dropout, and thus one cannot use classifier free guidance (cond_scale anything other than 1)")
+        self.cond_scale = float(cond_scale)
         self.im, self.unet_number, self.shape, self.noise = imagen, unet_number, tuple(shape), noise
         self.unet = unet = imagen.unets[unet_number - 1]
         spec = imagen.noise_schedulers[unet_number - 1]
@@ -120,6 +122,9 @@ class StageRun:
             self.inpaint = resize_image_to(imagen.normalize_img(inpaint_images.float()), S).contiguous()
             self.mask_u8 = resize_image_to(inpaint_masks[:, None].float(), S).bool()[:, 0].to(torch.uint8).contiguous()
         self.ex = unet.executor()
+        if self.cond_scale != 1.0:  # classifier-free guidance (sample.py:59): also prepare the null-conditioning context
+            self.ex.set_conditioning(cond_images=cond_images, lowres_cond_img=lowres_cond_img, text_embeds=text_embeds, text_mask=text_mask,
+                                     cond_drop_prob=1.0, image_size=S)
         self.ex.set_conditioning(cond_images=cond_images, lowres_cond_img=lowres_cond_img, text_embeds=text_embeds, text_mask=text_mask,
                                  cond_drop_prob=0.0, image_size=S)
         self.lowres_t = None
@@ -139,6 +144,9 @@ class StageRun:
             ops.inpaint_blend(self.img, self.inpaint, self.mask_u8, self.noise("inpaint", self.shape, self.device, unet=n, step=step, r=r),
                               sc["alpha"], sc["sigma"])
         pred = im._unet_step(self.unet, self.img, self.time_table[step], self.lowres_t, self.B, self.S)
+        if self.cond_scale != 1.0:  # Unet.forward_with_cond_scale: null + (cond - null) * scale
+            null = im._unet_step(self.unet, self.img, self.time_table[step], self.lowres_t, self.B, self.S, drop=1.0)
+            pred = ops.axpby(pred, null, self.cond_scale, 1.0 - self.cond_scale)
         s = None
         if self.dynamic_threshold:
             s = ops.dynthresh(self.img, pred, self.objective, sc["alpha"], sc["sigma"], im.dynamic_thresholding_percentile, self.ws)
@@ -231,16 +239,17 @@ class Imagen(nn.Module):
         raise NotImplementedError("training (Imagen.forward / loss) is outside the sampling hot path built here")
 
     # ------------------------------------------------------------------ one stage
-    def _unet_step(self, unet, img, time_row, lowres_t, B, S):
+    def _unet_step(self, unet, img, time_row, lowres_t, B, S, drop=0.0):
         ex = unet.executor()
         if not self.use_cuda_graph:
-            return ex.forward(img, time_row, lowres_t)
-        key = (id(ex), B, S, exists(ex.init_base), exists(ex.lowres_img), exists(getattr(ex, 'text', None)))
+            return ex.forward(img, time_row, lowres_t, drop=drop)
+        has_text = float(drop) in ex.text_by_drop
+        key = (id(ex), B, S, exists(ex.init_base), exists(ex.lowres_img), float(drop) if has_text else None)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) > 8:
                 self._graphs.clear()
-            g = self._graphs[key] = _StepGraph(ex, B, S, self.channels, lowres_t, img.device)
+            g = self._graphs[key] = _StepGraph(ex, B, S, self.channels, lowres_t, img.device, drop=drop)
         return g(img, time_row, lowres_t)
 
     def stage_run(self, unet_number, shape, *, noise, lowres_cond_img=None, lowres_noise_level=None, text_embeds=None, text_mask=None,

@@ -301,6 +301,27 @@ def attn_cross(q, kv, null_kv, heads, scale):
     return out
 
 
+def attn_small_f32(q, kv, heads, scale):
+    """q: fp32 [B,Nq,heads*64]; kv: fp32 [B,J,2*heads*64] (k | v) -> fp32 [B,Nq,heads*64]."""
+    _chk(q, torch.float32, "q")
+    _chk(kv, torch.float32, "kv")
+    B, Nq, _ = q.shape
+    out = torch.empty_like(q)
+    check(lib().kd_attn_small_f32(_ptr(q), _ptr(kv), _ptr(out), B, Nq, kv.shape[1], heads, scale, _stream()), "kd_attn_small_f32")
+    _count()
+    return out
+
+
+def axpby(x, y, a, b):
+    _chk(x, torch.float32, "x")
+    _chk(y, torch.float32, "y")
+    assert x.shape == y.shape
+    out = torch.empty_like(x)
+    check(lib().kd_axpby(_ptr(x), _ptr(y), float(a), float(b), _ptr(out), x.numel(), _stream()), "kd_axpby")
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ edge convs
 def im2col_nchw(x, ksize, Kp):
     _chk(x, torch.float32, "x")

@@ -207,8 +207,10 @@ class Unet(nn.Module):
         logits = self.forward(*args, **kwargs)
         if cond_scale == 1:
             return logits
+        from . import ops
+
         null_logits = self.forward(*args, cond_drop_prob=1.0, **kwargs)
-        return null_logits + (logits - null_logits) * cond_scale
+        return ops.axpby(logits, null_logits, cond_scale, 1.0 - cond_scale)  # null + (logits - null) * cond_scale
 
     @torch.no_grad()
     def forward(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None, cond_images=None,

@@ -190,3 +190,67 @@ def test_full_width_u3_forward_parity(cuda_lib):
     print(f"[full-width u3 @128] unet output rel_l2 = {err:.3e}")
     _report(taps_dev, taps_ref)
     assert err < TOL
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 2
+COND_U1 = dict(dim=64, dim_mults=(1, 2, 3, 4), cond_dim=128, text_embed_dim=3, num_resnet_blocks=2, layer_attns=(False, True, True, True),
+               layer_cross_attns=(False, True, True, True), cond_images_channels=4)
+COND_U2 = dict(dim=64, cond_dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=2, memory_efficient=True, layer_attns=(False, False, False, True),
+               layer_cross_attns=(False, False, True, True), init_conv_to_final_conv_residual=True, cond_images_channels=4)
+
+
+def _cond_pair():
+    from kidney_diffusion_b200 import Imagen, Unet
+    from oracle import imagen_oracle as O
+
+    torch.manual_seed(31)
+    oi = O.Imagen(unets=(O.Unet(**COND_U1), O.Unet(**COND_U2)), image_sizes=(32, 64), timesteps=(4, 3), pred_objectives=("noise", "v"),
+                  text_embed_dim=3)
+    O.randomize_zero_init_(oi)
+    pi = Imagen(unets=(Unet(**COND_U1), Unet(**COND_U2)), image_sizes=(32, 64), timesteps=(4, 3), pred_objectives=("noise", "v"),
+                text_embed_dim=3, random_crop_sizes=(None, None))
+    pi.load_state_dict(oi.state_dict())
+    return oi.eval(), pi.cuda().eval()
+
+
+@pytest.mark.parametrize("cond_scale", [1.0, 3.0])
+def test_mask_and_clinical_vector_conditioned_cascade(cuda_lib, cond_scale):
+    """Config 2 (sample_cond.py:37-48): text_embeds = clinical vector [0.0, 0.5, 0.2] per sample, cond_images = 4-channel one-hot
+    label map, base + SR stage; cond_scale = 3 additionally exercises classifier-free guidance (sample.py:59)."""
+    oi, pi = _cond_pair()
+    B = 3
+    g = torch.Generator().manual_seed(1)
+    conds = torch.tensor([0.0, 0.5, 0.2]).reshape(1, 1, 3).repeat_interleave(B, dim=0)
+    labels = torch.randint(0, 5, (B, 128, 128), generator=g)
+    deep = torch.stack([(labels == k).float() for k in range(1, 5)], dim=1)
+    kn = KeyedNoise(17)
+    ref_steps = []
+    ref = oi.sample(text_embeds=conds, cond_images=deep, cond_scale=cond_scale, noise_fn=kn.cpu, step_taps=ref_steps)
+    pi.noise_fn = kn.dev
+    out = pi.sample(text_embeds=conds, cond_images=deep, cond_scale=cond_scale, use_tqdm=False, device="cuda")
+    err = rel_l2(out, ref)
+    print(f"config-2 cascade (cond_scale {cond_scale}): final rel_l2 = {err:.3e}")
+    assert out.shape == (B, 3, 64, 64) and err < TOL
+
+
+def test_text_conditioning_tower_parity(cuda_lib):
+    """Unet.forward with text: conditioning tokens c and time conditioning t against the oracle, keep and drop branches."""
+    oi, pi = _cond_pair()
+    ou, pu = oi.unets[0], pi.unets[0]
+    B = 2
+    g = torch.Generator().manual_seed(2)
+    x, t = torch.randn(B, 3, 32, 32, generator=g), torch.tensor([1.5, -2.0])
+    te = torch.randn(B, 2, 3, generator=g)
+    tm = torch.tensor([[True, True], [True, False]])
+    cond = torch.rand(B, 4, 32, 32, generator=g)
+    for drop in (0.0, 1.0):
+        taps_ref, taps_dev = {}, {}
+        with torch.no_grad():
+            ref = ou(x, t, text_embeds=te, text_mask=tm, cond_images=cond, cond_drop_prob=drop, taps=taps_ref)
+        ex = pu.executor()
+        ex.set_conditioning(cond_images=cond.cuda(), lowres_cond_img=None, text_embeds=te.cuda(), text_mask=tm.cuda(), cond_drop_prob=drop,
+                            image_size=32)
+        out = ex.forward(x.cuda(), t.cuda(), None, taps=taps_dev)
+        e_t, e_c, e_o = rel_l2(taps_dev["t"], taps_ref["t"]), rel_l2(taps_dev["c"], taps_ref["c"]), rel_l2(out, ref)
+        print(f"drop={drop}: t {e_t:.2e} c {e_c:.2e} out {e_o:.2e}")
+        assert e_t < 1e-5 and e_c < 1e-5 and e_o < TOL
