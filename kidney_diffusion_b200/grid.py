@@ -328,7 +328,7 @@ def generate_image_with_unet(mag_level, unet_number, args, lowres_image, cond_im
     device = _device_for(args, rank)
     imagen = load_model(mag_level, unet_number, device, args)
     S = PATCH_SIZES[unet_number]
-    n = cond_image.shape[0] if cond_image is not None else 1
+    n = len(patch_pos) if patch_pos is not None else (cond_image.shape[0] if cond_image is not None else 1)
     sample_kw = dict(return_pil_images=False, start_at_unet_number=unet_number, stop_at_unet_number=unet_number,
                      inpaint_resample_times=args.inpaint_resample, use_tqdm=False, device=device)
 
@@ -346,7 +346,7 @@ def generate_image_with_unet(mag_level, unet_number, args, lowres_image, cond_im
     sched = build_schedule(patch_pos, orientation, world, max(1, min(getattr(args, "max_batch", None) or MAX_BATCH[unet_number], n)))
     owner = sched.owner
     overlap_pos = int(overlap * S)
-    patch_width = get_patch_width(args, mag_level)
+    patch_width = get_patch_width(args, mag_level) if cond_image is not None else 0  # only used for fallback neighbour crops
     patch_dist = int(patch_width * (1 - overlap))
 
     # previous-stage outputs must sit on the rank that runs the patch now
@@ -378,7 +378,8 @@ def generate_image_with_unet(mag_level, unet_number, args, lowres_image, cond_im
                             g = ghosts[(kk, kind)]
                             strips[kind] = (g, g.shape[1] * g.shape[2], g.shape[2])
                     else:
-                        fb = _fallback_neighbour(kind, (i, j), orientation, num_patches_width, cond_image[k], patch_width, patch_dist, S, device)
+                        fb = _fallback_neighbour(kind, (i, j), orientation, num_patches_width, None if cond_image is None else cond_image[k],
+                                                 patch_width, patch_dist, S, device)
                         strips[kind] = None if fb is None else _strip_of(fb, kind, S, overlap_pos, orientation)
                 ip, im = CANVAS_FN(S, overlap_pos, orientation, strips["above"], strips["side"], strips["corner"], device)
                 inpaints.append(ip)
@@ -402,7 +403,8 @@ def generate_image_with_unet(mag_level, unet_number, args, lowres_image, cond_im
 
 
 def _noise_key(mag_level, idx):
-    return (mag_level << 24) | idx
+    mag = mag_level if isinstance(mag_level, int) else 7  # "outpaint" grid
+    return (mag << 24) | idx
 
 
 def _fallback_neighbour(kind, pos, orientation, num_patches_width, cond_image, patch_width, patch_dist, S, device):
@@ -412,7 +414,7 @@ def _fallback_neighbour(kind, pos, orientation, num_patches_width, cond_image, p
     space_above = i != 0
     space_side = (orientation == 1 and j < num_patches_width - 1) or (orientation == -1 and j > 0)
     ok = dict(above=space_above, side=space_side, corner=space_above and space_side)[kind]
-    if not ok:
+    if not ok or cond_image is None:
         return None
     ty = cond_image.shape[1] // 2 - patch_width // 2
     tx = cond_image.shape[2] // 2 - patch_width // 2
