@@ -25,6 +25,7 @@ constexpr int NUM_THREADS = 192;
 
 struct ConvParams {
   int mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, out_f32, addend_f32;
+  int dbg_skip_a;  // timing experiment only (kd_set_conv_impl(3)): load the A tile for one tap in three
   int TW, TH, TB;
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int chunks_a, chunks_per_tap, num_kb;
@@ -478,6 +479,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_smem = smem_base + STAGES * STAGE_BYTES;  // 2 x 16 KB swizzled output staging (1024-aligned)
   uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES;
+  float* epi_aux = reinterpret_cast<float*>(ctrl + 256);  // per epilogue set: bias[64] + gate[2][64]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -536,14 +538,16 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb_local = smem_u32(&full_bar[s]);
           const uint32_t fb_leader = fb_local & kPeerBitMask;
-          if (rank == 0) mbar_expect_tx(fb_local, 2 * STAGE_BYTES);
           const int tap = kb / p.chunks_per_tap;
+          const bool load_a = !p.dbg_skip_a || (tap % 3 == 0);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * (load_a ? STAGE_BYTES : B_HALF_BYTES));
           const int ch = kb - tap * p.chunks_per_tap;
           const bool src_b = ch >= p.chunks_a;
           const CUtensorMap* map = src_b ? &map_b : &map_a;
           const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-          if (p.mode == 1) {
+          if (!load_a) {
+          } else if (p.mode == 1) {
             const int dy = tap >> 1, dx = tap & 1;
             const int C = src_b ? p.Cb : p.Ca;
             tma_load_5d_2sm(a_dst, map, fb_leader, dx * C + c0, w0, dy, h0, b0);
@@ -588,6 +592,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int set = (warp - 4) >> 2;
     const bool issuer = (quarter == 0) && (lane == 0);  // this set's TMA-store thread
     const uint32_t stage = epi_smem + set * EPI_STAGE_BYTES;
+    float* bias_s = epi_aux + set * (3 * EPI_COLS);
+    float* gate_s = bias_s + EPI_COLS;
     const int r = quarter * 32 + lane;
     const int tw = r % p.TW;
     const int th = (r / p.TW) % p.TH;
@@ -641,18 +647,35 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int q = 0; q < 8; ++q) addv[q] = (nc0 + q * 8 + 8 <= p.Cout) ? ld_stream(ap + q) : make_int4(0, 0, 0, 0);
           }
+          // bias (and the GlobalContext gate rows of the <= 2 batch images a tile can touch) for these 64 columns go through
+          // smem: per-element global / L1 loads inside the math loop stalled the 8 epilogue warps (ncu: long scoreboard)
+          const bool gate_smem = (p.addend_scale != nullptr) && (p.TB <= 2);
+          if (r < EPI_COLS) {
+            bias_s[r] = (p.bias != nullptr && nc0 + r < p.Cout) ? __ldg(p.bias + nc0 + r) : 0.f;
+          } else if (gate_smem) {
+            const int c = r - EPI_COLS;
+#pragma unroll
+            for (int t2 = 0; t2 < 2; ++t2) {
+              const int bb = tile_b * p.TB + t2;
+              gate_s[t2 * EPI_COLS + c] = (bb < p.B && nc0 + c < p.Cout) ? p.addend_scale[(long long)bb * p.Cout + nc0 + c] : 0.f;
+            }
+          }
           // the TMA store that last read this set's staging buffer must have finished reading it
           if (issuer) tma_store_wait_read<0>();
           epi_barrier(set);
+          uint32_t acc2[2][32];
+          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS), acc2[0]);
+          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + 32), acc2[1]);
+          tmem_ld_wait();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + half * 32), acc);
-            tmem_ld_wait();
+            const uint32_t* acc = acc2[half];
             const int nc = nc0 + half * 32;
-            const float* gate = p.addend_scale ? p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc : nullptr;
+            const float* gate = nullptr;
+            if (p.addend_scale != nullptr)
+              gate = gate_smem ? (gate_s + tb * EPI_COLS + half * 32) : (p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc);
             long long add_off = 0;
-            if (p.addend != nullptr && row_ok) {
+            if (p.addend != nullptr && row_ok && p.addend_f32) {
               if (p.out_mode == 1) {
                 const int q4 = nc / Cq, c = nc - q4 * Cq;
                 add_off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
@@ -663,14 +686,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 4 groups of 8 columns -> one 16-byte staging store each
               float v[8];
-              if (p.bias != nullptr && nc + q * 8 + 8 <= p.Cout) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + q * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + q * 8 + 4));
-                v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = 0.f;
-              }
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8 + 4);
+              v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[q * 8 + j]) + v[j], p.act);
               if (p.addend != nullptr && row_ok && nc + q * 8 + 8 <= p.Cout) {
@@ -827,7 +845,8 @@ int make_out_map(CUtensorMap* m, const ConvParams& p, void* out) {
 
 template <int BN, int STAGES>
 int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 2 * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 2 * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                       2 * 3 * EPI_COLS * 4 /*bias + gate staging*/;
   static_assert(SMEM <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
   CUtensorMap mo = ma;
   if (!p.out_f32) {
@@ -853,12 +872,12 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   return KD_OK;
 }
 
-int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel (kd_set_conv_impl)
+int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel, 3 = pair kernel + skip-A timing experiment
 
 }  // namespace
 
 extern "C" int kd_set_conv_impl(int impl) {
-  if (impl < 0 || impl > 2) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0, 1 or 2");
+  if (impl < 0 || impl > 3) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0..3");
   g_conv_impl = impl;
   return KD_OK;
 }
@@ -899,7 +918,8 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
   p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out;
 
   // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel
-  const bool use_pair = (g_conv_impl == 2) || (g_conv_impl == 0 && d->Cout >= 128);
+  const bool use_pair = (g_conv_impl == 2) || ((g_conv_impl == 0 || g_conv_impl == 3) && d->Cout >= 128);
+  p.dbg_skip_a = (g_conv_impl == 3) ? 1 : 0;
   KD_REQUIRE(!(g_conv_impl == 2 && d->Cout < 128), "kd_conv_gemm: the CTA-pair kernel needs Cout >= 128");
   const int BN = use_pair ? (d->Cout >= 256 ? 256 : 128) : (d->Cout >= 128 ? 128 : 64);
   p.n_tiles = kd_ceil_div(d->Cout, BN);

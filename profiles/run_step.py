@@ -33,6 +33,8 @@ torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("launches in profiled step:", ops.launch_count - n0)
 
+if os.environ.get("KD_CONV_IMPL"):
+    ops.set_conv_impl(int(os.environ["KD_CONV_IMPL"]))
 if os.environ.get("KD_CONV_TABLE"):
     import collections
 
