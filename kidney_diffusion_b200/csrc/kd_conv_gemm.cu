@@ -121,11 +121,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 "version 1"):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 (8 rows * 128 B = 1024)
 //   [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
@@ -463,6 +463,164 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
   }
 }
 
+// ---- epilogue role of the CTA-pair kernels (warps 4..11): drains the double-buffered TMEM accumulator tile by tile
+template <int BN>
+__device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CUtensorMap* map_out_ptr, const uint32_t tmem_base,
+                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const uint32_t epi_smem,
+                                                   float* epi_aux, const int warp, const int lane, const uint32_t rank,
+                                                   const int cluster_id, const int num_clusters, const int num_pair_tiles) {
+  const CUtensorMap& map_out = *map_out_ptr;
+  // ================================================================ epilogue (both CTAs): own 128 rows x BN columns
+  // two sets of 4 warps (one warp of each set per SM sub-partition): set 0 takes the even 64-column groups, set 1 the odd
+  const int quarter = warp & 3;
+  const int set = (warp - 4) >> 2;
+  const bool issuer = (quarter == 0) && (lane == 0);  // this set's TMA-store thread
+  const uint32_t stage = epi_smem + set * EPI_STAGE_BYTES;
+  float* bias_s = epi_aux + set * (3 * EPI_COLS);
+  float* gate_s = bias_s + EPI_COLS;
+  const int r = quarter * 32 + lane;
+  const int tw = r % p.TW;
+  const int th = (r / p.TW) % p.TH;
+  const int tb = r / (p.TW * p.TH);
+  uint32_t tile_iter = 0;
+  for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
+    const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+    const int n_tile = t % p.n_tiles;
+    int m_tile = (t / p.n_tiles) * 2 + (int)rank;
+    const int tile_w = m_tile % p.tiles_w;
+    m_tile /= p.tiles_w;
+    const int tile_h = m_tile % p.tiles_h;
+    const int tile_b = m_tile / p.tiles_h;
+    const int b = tile_b * p.TB + tb, h = tile_h * p.TH + th, w = tile_w * p.TW + tw;
+    const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
+    const int n0 = n_tile * BN;
+
+    mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+    tc_fence_after();
+    if (p.out_f32) {
+      // fp32 output (tests / small tensors): direct per-row stores
+#pragma unroll 1
+      for (int chunk = set; chunk < BN / 32; chunk += 2) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
+        tmem_ld_wait();
+        const int nc = n0 + chunk * 32;
+        if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
+      }
+    } else {
+      // h16 output: 64-column groups staged in 128B-swizzled smem and written with one coalesced TMA store each
+      const bool tile_in_range = tile_b < p.tiles_b;
+      const int Cq = p.Cout >> 2;
+#pragma unroll 1
+      for (int g = set; g < BN / EPI_COLS; g += 2) {
+        const int nc0 = n0 + g * EPI_COLS;
+        if (nc0 >= p.Cout) break;  // uniform across the set
+        // prefetch this row's 64 addend values (8 x 16 B) before any waiting: their latency hides behind the barrier
+        // and the TMEM load
+        int4 addv[8];
+        const bool has_add = (p.addend != nullptr) && row_ok && !p.addend_f32;
+        if (has_add) {
+          long long off;
+          if (p.out_mode == 1) {
+            const int q4 = nc0 / Cq, c = nc0 - q4 * Cq;
+            off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
+          } else {
+            off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc0;
+          }
+          const int4* ap = reinterpret_cast<const int4*>(reinterpret_cast<const h16*>(p.addend) + off);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) addv[q] = (nc0 + q * 8 + 8 <= p.Cout) ? ld_stream(ap + q) : make_int4(0, 0, 0, 0);
+        }
+        // bias (and the GlobalContext gate rows of the <= 2 batch images a tile can touch) for these 64 columns go through
+        // smem: per-element global / L1 loads inside the math loop stalled the 8 epilogue warps (ncu: long scoreboard)
+        const bool gate_smem = (p.addend_scale != nullptr) && (p.TB <= 2);
+        if (r < EPI_COLS) {
+          bias_s[r] = (p.bias != nullptr && nc0 + r < p.Cout) ? __ldg(p.bias + nc0 + r) : 0.f;
+        } else if (gate_smem) {
+          const int c = r - EPI_COLS;
+#pragma unroll
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const int bb = tile_b * p.TB + t2;
+            gate_s[t2 * EPI_COLS + c] = (bb < p.B && nc0 + c < p.Cout) ? p.addend_scale[(long long)bb * p.Cout + nc0 + c] : 0.f;
+          }
+        }
+        // the TMA store that last read this set's staging buffer must have finished reading it
+        if (issuer) tma_store_wait_read<0>();
+        epi_barrier(set);
+        uint32_t acc2[2][32];
+        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS), acc2[0]);
+        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + 32), acc2[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* acc = acc2[half];
+          const int nc = nc0 + half * 32;
+          const float* gate = nullptr;
+          if (p.addend_scale != nullptr)
+            gate = gate_smem ? (gate_s + tb * EPI_COLS + half * 32) : (p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc);
+          long long add_off = 0;
+          if (p.addend != nullptr && row_ok && p.addend_f32) {
+            if (p.out_mode == 1) {
+              const int q4 = nc / Cq, c = nc - q4 * Cq;
+              add_off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
+            } else {
+              add_off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // 4 groups of 8 columns -> one 16-byte staging store each
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8 + 4);
+            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[q * 8 + j]) + v[j], p.act);
+            if (p.addend != nullptr && row_ok && nc + q * 8 + 8 <= p.Cout) {
+              float a[8];
+              if (p.addend_f32) {
+                const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + add_off + q * 8);
+                float4 a0 = ap[0], a1 = ap[1];
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+              } else {
+                h16x8_to_float(*reinterpret_cast<const h16x8*>(&addv[half * 4 + q]), a);
+              }
+              if (gate != nullptr) {
+                const float4 g0 = *reinterpret_cast<const float4*>(gate + q * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(gate + q * 8 + 4);
+                a[0] *= g0.x; a[1] *= g0.y; a[2] *= g0.z; a[3] *= g0.w; a[4] *= g1.x; a[5] *= g1.y; a[6] *= g1.z; a[7] *= g1.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += a[j];
+            }
+            const uint32_t chunk16 = (uint32_t)(half * 4 + q);
+            const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
+            const h16x8 o8 = float_to_h16x8(v);
+            const int4 ov = *reinterpret_cast<const int4*>(&o8);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z), "r"(ov.w) : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        epi_barrier(set);
+        if (issuer) {
+          if (tile_in_range) {
+            if (p.out_mode == 1) {
+              const int q4 = nc0 / Cq, c0 = nc0 - q4 * Cq;
+              tma_store_5d(&map_out, stage, (q4 & 1) * Cq + c0, tile_w * p.TW, q4 >> 1, tile_h * p.TH, tile_b * p.TB);
+            } else {
+              tma_store_5d(&map_out, stage, nc0, tile_w * p.TW, tile_h * p.TH, tile_b * p.TB, 0);
+            }
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_remote_arrive(smem_u32(&tmem_empty_bar[as]), 0);  // accumulator stage drained (leader's barrier)
+  }
+  if (issuer) tma_store_wait_read<0>();  // staging smem must outlive the last bulk stores
+}
+
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -586,159 +744,176 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogue (both CTAs): own 128 rows x BN columns
-    // two sets of 4 warps (one warp of each set per SM sub-partition): set 0 takes the even 64-column groups, set 1 the odd
-    const int quarter = warp & 3;
-    const int set = (warp - 4) >> 2;
-    const bool issuer = (quarter == 0) && (lane == 0);  // this set's TMA-store thread
-    const uint32_t stage = epi_smem + set * EPI_STAGE_BYTES;
-    float* bias_s = epi_aux + set * (3 * EPI_COLS);
-    float* gate_s = bias_s + EPI_COLS;
-    const int r = quarter * 32 + lane;
-    const int tw = r % p.TW;
-    const int th = (r / p.TW) % p.TH;
-    const int tb = r / (p.TW * p.TH);
-    uint32_t tile_iter = 0;
-    for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
-      const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
-      const int n_tile = t % p.n_tiles;
-      int m_tile = (t / p.n_tiles) * 2 + (int)rank;
-      const int tile_w = m_tile % p.tiles_w;
-      m_tile /= p.tiles_w;
-      const int tile_h = m_tile % p.tiles_h;
-      const int tile_b = m_tile / p.tiles_h;
-      const int b = tile_b * p.TB + tb, h = tile_h * p.TH + th, w = tile_w * p.TW + tw;
-      const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
-      const int n0 = n_tile * BN;
-
-      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
-      tc_fence_after();
-      if (p.out_f32) {
-        // fp32 output (tests / small tensors): direct per-row stores
-#pragma unroll 1
-        for (int chunk = set; chunk < BN / 32; chunk += 2) {
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
-          tmem_ld_wait();
-          const int nc = n0 + chunk * 32;
-          if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
-        }
-      } else {
-        // h16 output: 64-column groups staged in 128B-swizzled smem and written with one coalesced TMA store each
-        const bool tile_in_range = tile_b < p.tiles_b;
-        const int Cq = p.Cout >> 2;
-#pragma unroll 1
-        for (int g = set; g < BN / EPI_COLS; g += 2) {
-          const int nc0 = n0 + g * EPI_COLS;
-          if (nc0 >= p.Cout) break;  // uniform across the set
-          // prefetch this row's 64 addend values (8 x 16 B) before any waiting: their latency hides behind the barrier
-          // and the TMEM load
-          int4 addv[8];
-          const bool has_add = (p.addend != nullptr) && row_ok && !p.addend_f32;
-          if (has_add) {
-            long long off;
-            if (p.out_mode == 1) {
-              const int q4 = nc0 / Cq, c = nc0 - q4 * Cq;
-              off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
-            } else {
-              off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc0;
-            }
-            const int4* ap = reinterpret_cast<const int4*>(reinterpret_cast<const h16*>(p.addend) + off);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) addv[q] = (nc0 + q * 8 + 8 <= p.Cout) ? ld_stream(ap + q) : make_int4(0, 0, 0, 0);
-          }
-          // bias (and the GlobalContext gate rows of the <= 2 batch images a tile can touch) for these 64 columns go through
-          // smem: per-element global / L1 loads inside the math loop stalled the 8 epilogue warps (ncu: long scoreboard)
-          const bool gate_smem = (p.addend_scale != nullptr) && (p.TB <= 2);
-          if (r < EPI_COLS) {
-            bias_s[r] = (p.bias != nullptr && nc0 + r < p.Cout) ? __ldg(p.bias + nc0 + r) : 0.f;
-          } else if (gate_smem) {
-            const int c = r - EPI_COLS;
-#pragma unroll
-            for (int t2 = 0; t2 < 2; ++t2) {
-              const int bb = tile_b * p.TB + t2;
-              gate_s[t2 * EPI_COLS + c] = (bb < p.B && nc0 + c < p.Cout) ? p.addend_scale[(long long)bb * p.Cout + nc0 + c] : 0.f;
-            }
-          }
-          // the TMA store that last read this set's staging buffer must have finished reading it
-          if (issuer) tma_store_wait_read<0>();
-          epi_barrier(set);
-          uint32_t acc2[2][32];
-          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS), acc2[0]);
-          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + 32), acc2[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t* acc = acc2[half];
-            const int nc = nc0 + half * 32;
-            const float* gate = nullptr;
-            if (p.addend_scale != nullptr)
-              gate = gate_smem ? (gate_s + tb * EPI_COLS + half * 32) : (p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc);
-            long long add_off = 0;
-            if (p.addend != nullptr && row_ok && p.addend_f32) {
-              if (p.out_mode == 1) {
-                const int q4 = nc / Cq, c = nc - q4 * Cq;
-                add_off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
-              } else {
-                add_off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc;
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {  // 4 groups of 8 columns -> one 16-byte staging store each
-              float v[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8 + 4);
-              v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[q * 8 + j]) + v[j], p.act);
-              if (p.addend != nullptr && row_ok && nc + q * 8 + 8 <= p.Cout) {
-                float a[8];
-                if (p.addend_f32) {
-                  const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + add_off + q * 8);
-                  float4 a0 = ap[0], a1 = ap[1];
-                  a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-                } else {
-                  h16x8_to_float(*reinterpret_cast<const h16x8*>(&addv[half * 4 + q]), a);
-                }
-                if (gate != nullptr) {
-                  const float4 g0 = *reinterpret_cast<const float4*>(gate + q * 8);
-                  const float4 g1 = *reinterpret_cast<const float4*>(gate + q * 8 + 4);
-                  a[0] *= g0.x; a[1] *= g0.y; a[2] *= g0.z; a[3] *= g0.w; a[4] *= g1.x; a[5] *= g1.y; a[6] *= g1.z; a[7] *= g1.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += a[j];
-              }
-              const uint32_t chunk16 = (uint32_t)(half * 4 + q);
-              const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
-              const h16x8 o8 = float_to_h16x8(v);
-              const int4 ov = *reinterpret_cast<const int4*>(&o8);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z), "r"(ov.w) : "memory");
-            }
-          }
-          fence_proxy_async_smem();
-          epi_barrier(set);
-          if (issuer) {
-            if (tile_in_range) {
-              if (p.out_mode == 1) {
-                const int q4 = nc0 / Cq, c0 = nc0 - q4 * Cq;
-                tma_store_5d(&map_out, stage, (q4 & 1) * Cq + c0, tile_w * p.TW, q4 >> 1, tile_h * p.TH, tile_b * p.TB);
-              } else {
-                tma_store_5d(&map_out, stage, nc0, tile_w * p.TW, tile_h * p.TH, tile_b * p.TB, 0);
-              }
-            }
-            tma_store_commit();
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_remote_arrive(smem_u32(&tmem_empty_bar[as]), 0);  // accumulator stage drained (leader's barrier)
-    }
-    if (issuer) tma_store_wait_read<0>();  // staging smem must outlive the last bulk stores
+    pair_epilogue_role<BN>(p, &map_out, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
+                           num_clusters, num_pair_tiles);
   }
 
   tc_fence_before();
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its partner can still signal its barriers / read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ================================================================================================ conv v3 (3x3, halo reuse)
+// Same CTA-pair / persistent / double-buffered-TMEM structure as conv_gemm_pair_kernel, but the A operand of all nine taps
+// of a 64-channel chunk comes from ONE halo tile in shared memory: the CTA's M tile is 16 rows x 8 columns of pixels, the
+// TMA box is the (16+2) x (8+2) pixel halo (180 rows of 128 B, out-of-bounds = zero padding), and tap (ky,kx) is the UMMA
+// descriptor with start address + (ky*10 + kx) * 128 B and SBO = 10 * 128 B (next 8-pixel group = next image row).  This
+// works because the 128-byte swizzle is a function of the absolute shared-memory address for both the TMA write and the
+// tcgen05.mma read (verified on B200 by profiles/halo_probe.py: rel-L2 7e-7).  L2 -> SMEM traffic per k-block drops from
+// 16 KB (A) + B to 2.5 KB + B, which is what bounded the tap-loop kernel (profiles/README.md).
+//
+// Two operand rings: A halo tiles (HALO_AS stages, one per 64-channel chunk) and weight tiles (BS stages, one per tap).
+constexpr int HALO_TW = 8, HALO_TH = 16, HALO_W = HALO_TW + 2, HALO_H = HALO_TH + 2;
+constexpr int HALO_BYTES = HALO_H * HALO_W * 128;                 // 23 040 B actually transferred per chunk
+constexpr int HALO_STAGE_BYTES = ((HALO_BYTES + 1023) / 1024) * 1024;  // stage stride keeps 1024-byte alignment
+constexpr int HALO_AS = 3;
+
+template <int BN, int BS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const ConvParams p,
+                      const int num_pair_tiles) {
+  constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + HALO_AS * HALO_STAGE_BYTES;
+  const uint32_t epi_smem = b_base + BS * B_HALF_BYTES;
+  uint8_t* ctrl = smem_gen + HALO_AS * HALO_STAGE_BYTES + BS * B_HALF_BYTES + 2 * EPI_STAGE_BYTES;
+  float* epi_aux = reinterpret_cast<float*>(ctrl + 256);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* a_empty = a_full + HALO_AS;
+  uint64_t* b_full = a_empty + HALO_AS;
+  uint64_t* b_empty = b_full + BS;
+  uint64_t* tmem_full_bar = b_empty + BS;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  static_assert((2 * HALO_AS + 2 * BS + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int Ctot = p.Ca + p.Cb;
+
+  cluster_sync_all();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_out);
+    if (p.Cb > 0) tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < HALO_AS; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 2);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+#pragma unroll
+    for (int s = 0; s < BS; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 2);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs, one lane each)
+    if (lane == 0) {
+      uint32_t ita = 0, itb = 0;
+      for (int t = cluster_id; t < num_pair_tiles; t += num_clusters) {
+        const int n_tile = t % p.n_tiles;
+        int m_tile = (t / p.n_tiles) * 2 + (int)rank;
+        const int tile_w = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int tile_h = m_tile % p.tiles_h;
+        const int tile_b = m_tile / p.tiles_h;
+        const int w0 = tile_w * HALO_TW, h0 = tile_h * HALO_TH;
+        const int n0 = n_tile * BN + (int)rank * (BN / 2);
+        for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
+          const uint32_t sa = ita % HALO_AS;
+          const uint32_t pha = (ita / HALO_AS) & 1;
+          mbar_wait(smem_u32(&a_empty[sa]), pha ^ 1u);
+          const uint32_t fa_local = smem_u32(&a_full[sa]);
+          if (rank == 0) mbar_expect_tx(fa_local, 2 * HALO_BYTES);
+          const bool src_b = ch >= p.chunks_a;
+          const CUtensorMap* map = src_b ? &map_b : &map_a;
+          const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
+          tma_load_5d_2sm(a_base + sa * HALO_STAGE_BYTES, map, fa_local & kPeerBitMask, c0, w0 - 1, h0 - 1, tile_b, 0);
+          if (rank != 0) mbar_remote_arrive(fa_local, 0);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++itb) {
+            const uint32_t sb = itb % BS;
+            const uint32_t phb = (itb / BS) & 1;
+            mbar_wait(smem_u32(&b_empty[sb]), phb ^ 1u);
+            const uint32_t fb_local = smem_u32(&b_full[sb]);
+            if (rank == 0) mbar_expect_tx(fb_local, 2 * B_HALF_BYTES);
+            tma_load_2d_2sm(b_base + sb * B_HALF_BYTES, &map_w, fb_local & kPeerBitMask, tap * Ctot + ch * BK, n0);
+            if (rank != 0) mbar_remote_arrive(fb_local, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA, one lane)
+    if (rank == 0 && lane == 0) {
+      uint32_t ita = 0, itb = 0, tile_iter = 0;
+      for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
+        const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
+          const uint32_t sa = ita % HALO_AS;
+          const uint32_t pha = (ita / HALO_AS) & 1;
+          mbar_wait(smem_u32(&a_full[sa]), pha);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + sa * HALO_STAGE_BYTES;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++itb) {
+            const uint32_t sb = itb % BS;
+            const uint32_t phb = (itb / BS) & 1;
+            mbar_wait(smem_u32(&b_full[sb]), phb);
+            tc_fence_after();
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint64_t a_desc = make_sw128_desc(a_stage + (uint32_t)(ky * HALO_W + kx) * 128u, HALO_W * 128);
+            const uint64_t b_desc = make_sw128_desc(b_base + sb * B_HALF_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (ch | tap | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(smem_u32(&b_empty[sb]));
+          }
+          umma_commit_2sm(smem_u32(&a_empty[sa]));
+        }
+        umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
+      }
+    }
+  } else if (warp >= 4) {
+    pair_epilogue_role<BN>(p, &map_out, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
+                           num_clusters, num_pair_tiles);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, TMEM_COLS);
@@ -793,7 +968,14 @@ int pow2_ceil(int v) {
 }
 
 // activation tensor map for one source with C channels
-int make_act_map(CUtensorMap* m, const KdConvDesc* d, const void* x, int C, int TW, int TH, int TB) {
+int make_act_map(CUtensorMap* m, const KdConvDesc* d, const void* x, int C, int TW, int TH, int TB, bool halo = false) {
+  if (halo) {  // one box = the (TH+2) x (TW+2) pixel halo of a 16 x 8 tile
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B, 1ull};
+    const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2,
+                             (uint64_t)d->B * d->H * d->W * C * 2};
+    const uint32_t box[5] = {(uint32_t)BK, (uint32_t)HALO_W, (uint32_t)HALO_H, 1u, 1u};
+    return encode_map(m, x, 5, dims, str, box);
+  }
   if (d->mode == 1) {
     const uint64_t Hi = 2ull * d->H, Wi = 2ull * d->W;
     const uint64_t dims[5] = {2ull * C, (uint64_t)d->W, 2ull, (uint64_t)d->H, (uint64_t)d->B};
@@ -872,12 +1054,39 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   return KD_OK;
 }
 
-int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel, 3 = pair kernel + skip-A timing experiment
+template <int BN, int BS>
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
+  constexpr int SMEM = HALO_AS * HALO_STAGE_BYTES + BS * (BN / 2) * BK * 2 + 2 * EPI_STAGE_BYTES + 1024 + 256 + 2 * 3 * EPI_COLS * 4;
+  static_assert(SMEM <= 232448, "halo kernel exceeds the 227 KB shared-memory limit");
+  CUtensorMap mo;
+  int rc = make_out_map(&mo, p, p.out);
+  if (rc) return rc;
+  static bool configured = false;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured) {
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured = true;
+    }
+  }
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  const long long pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+  KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
+  int clusters = kd_num_sms() / 2;
+  if (pair_tiles < clusters) clusters = (int)pair_tiles;
+  conv_gemm_halo_kernel<BN, BS><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, p, (int)pair_tiles);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = pair (halo where possible), 3 = tap-loop pair + skip-A timing
+                      // experiment, 4 = tap-loop pair kernel only (no halo reuse)
 
 }  // namespace
 
 extern "C" int kd_set_conv_impl(int impl) {
-  if (impl < 0 || impl > 3) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0..3");
+  if (impl < 0 || impl > 4) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0..4");
   g_conv_impl = impl;
   return KD_OK;
 }
@@ -917,10 +1126,21 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
   p.num_kb = taps * p.chunks_per_tap;
   p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out;
 
-  // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel
-  const bool use_pair = (g_conv_impl == 2) || ((g_conv_impl == 0 || g_conv_impl == 3) && d->Cout >= 128);
+  // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel;
+  // 3x3 convolutions on images of at least 16 x 8 pixels use the halo-reuse variant (impl 4 forces the tap-loop pair kernel)
+  const bool use_pair = (g_conv_impl == 2) || (g_conv_impl == 4) || ((g_conv_impl == 0 || g_conv_impl == 3) && d->Cout >= 128);
   p.dbg_skip_a = (g_conv_impl == 3) ? 1 : 0;
-  KD_REQUIRE(!(g_conv_impl == 2 && d->Cout < 128), "kd_conv_gemm: the CTA-pair kernel needs Cout >= 128");
+  KD_REQUIRE(!((g_conv_impl == 2 || g_conv_impl == 4) && d->Cout < 128), "kd_conv_gemm: the CTA-pair kernel needs Cout >= 128");
+  const bool use_halo = use_pair && g_conv_impl != 4 && g_conv_impl != 3 && d->mode == 0 && d->ksize == 3 && d->H >= HALO_TH &&
+                        d->W >= HALO_TW && !d->out_f32 && d->out_mode == 0;
+  if (use_halo) {  // 16 x 8 pixel tiles, one image per tile
+    p.TW = HALO_TW;
+    p.TH = HALO_TH;
+    p.TB = 1;
+    p.tiles_w = kd_ceil_div(d->W, p.TW);
+    p.tiles_h = kd_ceil_div(d->H, p.TH);
+    p.tiles_b = d->B;
+  }
   const int BN = use_pair ? (d->Cout >= 256 ? 256 : 128) : (d->Cout >= 128 ? 128 : 64);
   p.n_tiles = kd_ceil_div(d->Cout, BN);
   const long long grid = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
@@ -929,10 +1149,10 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
   KdConvDesc dd = *d;
   if (d->mode == 2) dd.mode = 0;
   CUtensorMap ma, mb, mw;
-  int rc = make_act_map(&ma, &dd, xa, d->Ca, p.TW, p.TH, p.TB);
+  int rc = make_act_map(&ma, &dd, xa, d->Ca, p.TW, p.TH, p.TB, use_halo);
   if (rc) return rc;
   if (d->Cb > 0) {
-    rc = make_act_map(&mb, &dd, xb, d->Cb, p.TW, p.TH, p.TB);
+    rc = make_act_map(&mb, &dd, xb, d->Cb, p.TW, p.TH, p.TB, use_halo);
     if (rc) return rc;
   } else {
     mb = ma;
@@ -944,6 +1164,10 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};  // pair kernel: each CTA loads half the tile rows
     rc = encode_map(&mw, w, 2, dims, str, box);
     if (rc) return rc;
+  }
+  if (use_halo) {
+    if (BN == 256) return launch_halo<256, 7>(ma, mb, mw, p, stream);
+    return launch_halo<128, 10>(ma, mb, mw, p, stream);
   }
   if (use_pair) {
     if (BN == 256) return launch_pair<256, 6>(ma, mb, mw, p, stream);

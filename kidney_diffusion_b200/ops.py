@@ -21,6 +21,27 @@ launch_count = 0  # kernels launched through this module (bench.py reports it as
 conv_profile = None  # bench.py sets this to a list: every tensor-core GEMM launch appends (flops, start_event, end_event)
 
 
+op_profile = None  # bench / profiling: list of (op name, start_event, end_event) for EVERY op when set
+
+
+def _timed(fn):
+    """CUDA-event bracket around an op while `op_profile` is a list (no cost otherwise)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if op_profile is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a, **k)
+        e1.record()
+        op_profile.append((fn.__name__, e0, e1))
+        return out
+
+    return wrapper
+
+
 class _ConvTimer:
     """CUDA-event bracket around one kd_conv_gemm launch on the launching stream (only active while profiling)."""
 
@@ -76,6 +97,7 @@ def set_conv_impl(impl):
     check(lib().kd_set_conv_impl(int(impl)), "kd_set_conv_impl")
 
 
+@_timed
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
               addend=None, addend_scale=None, out=None):
     """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32)."""
@@ -111,6 +133,7 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
     return out
 
 
+@_timed
 def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=None, algo_k=None):
     """Plain GEMM y[M,N] = act(x[M,K] @ w[N,K]^T + bias) + addend on tensor cores (mode 2)."""
     _chk(x, ACT_DTYPE, "x")
@@ -138,6 +161,7 @@ def gemm_rows(x, w, bias=None, *, act=ACT_NONE, out_f32=False, addend=None, out=
 
 
 # ------------------------------------------------------------------------------------------------ small linear / time embedding
+@_timed
 def linear_small(x, w, bias=None, *, pre_act=ACT_NONE, post_act=ACT_NONE, out=None, ldy=None):
     """fp32 y[M,N] = post(pre(x[M,K]) @ w[N,K]^T + bias); `out` may be a strided row view (ldy)."""
     _chk(w, torch.float32, "w")
@@ -158,6 +182,7 @@ def linear_small(x, w, bias=None, *, pre_act=ACT_NONE, post_act=ACT_NONE, out=No
     return out
 
 
+@_timed
 def sinu_emb(t, weights):
     _chk(t, torch.float32, "t")
     _chk(weights, torch.float32, "weights")
@@ -179,6 +204,7 @@ def _nblk(HW, C, B):
     return int(max(1, min(want, -(-HW // lanes))))
 
 
+@_timed
 def gn_stats(x, c_offset, group_size, num_groups):
     _chk(x, ACT_DTYPE, "x")
     B, H, W, C = x.shape
@@ -190,6 +216,7 @@ def gn_stats(x, c_offset, group_size, num_groups):
     return partial
 
 
+@_timed
 def gn_finalize(partial_a, scale_a, partial_b, scale_b, count, eps=1e-5):
     B, nblk_a, G, _ = partial_a.shape
     nblk_b = 0 if partial_b is None else partial_b.shape[1]
@@ -200,6 +227,7 @@ def gn_finalize(partial_a, scale_a, partial_b, scale_b, count, eps=1e-5):
     return mean_rstd
 
 
+@_timed
 def gn_apply(x, mean_rstd, gamma, beta, *, c_offset, group_size, num_groups, src_scale=1.0, scale_shift=None, ctot=None,
              act=ACT_SILU):
     _chk(x, ACT_DTYPE, "x")
@@ -218,6 +246,7 @@ def gn_apply(x, mean_rstd, gamma, beta, *, c_offset, group_size, num_groups, src
 
 
 # ------------------------------------------------------------------------------------------------ GlobalContext
+@_timed
 def rowdot(x, w, bias):
     _chk(x, ACT_DTYPE, "x")
     B, H, W, C = x.shape
@@ -227,6 +256,7 @@ def rowdot(x, w, bias):
     return out
 
 
+@_timed
 def gca_pool(x, logits):
     B, H, W, C = x.shape
     HW = H * W
@@ -240,6 +270,7 @@ def gca_pool(x, logits):
     return pooled
 
 
+@_timed
 def gate_residual(h, gate, res):
     _chk(h, ACT_DTYPE, "h")
     B, H, W, C = h.shape
@@ -250,6 +281,7 @@ def gate_residual(h, gate, res):
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
+@_timed
 def layernorm_h16(x, g, bias=None, residual=None, eps=1e-5):
     _chk(x, ACT_DTYPE, "x")
     C = x.shape[-1]
@@ -260,6 +292,7 @@ def layernorm_h16(x, g, bias=None, residual=None, eps=1e-5):
     return y
 
 
+@_timed
 def layernorm_f32(x, g, bias=None, eps=1e-5):
     _chk(x, torch.float32, "x")
     C = x.shape[-1]
@@ -271,6 +304,7 @@ def layernorm_f32(x, g, bias=None, eps=1e-5):
 
 
 # ------------------------------------------------------------------------------------------------ attention
+@_timed
 def kv_assemble(qkv, kv_col, ctx_kv, null_kv):
     """qkv: fp16 [B,N,ld]; ctx_kv: fp32 [B,Jc,128] or None; null_kv fp32 [2,64] -> fp16 [B, Jc+1+N, 128]."""
     B, N, ld = qkv.shape
@@ -281,6 +315,7 @@ def kv_assemble(qkv, kv_col, ctx_kv, null_kv):
     return out
 
 
+@_timed
 def attn_mqa(q, kv, heads, scale):
     """q: fp16 [B,N,ld] (first heads*64 columns are the queries); kv: fp16 [B,J,128]."""
     B, N, ld = q.shape
@@ -291,6 +326,7 @@ def attn_mqa(q, kv, heads, scale):
     return out
 
 
+@_timed
 def attn_cross(q, kv, null_kv, heads, scale):
     """q: fp16 [B,N,heads*64]; kv: fp32 [B,Jc,2*heads*64]; null_kv fp32 [2,64]."""
     B, N, ld = q.shape
@@ -301,6 +337,7 @@ def attn_cross(q, kv, null_kv, heads, scale):
     return out
 
 
+@_timed
 def attn_small_f32(q, kv, heads, scale):
     """q: fp32 [B,Nq,heads*64]; kv: fp32 [B,J,2*heads*64] (k | v) -> fp32 [B,Nq,heads*64]."""
     _chk(q, torch.float32, "q")
@@ -312,6 +349,7 @@ def attn_small_f32(q, kv, heads, scale):
     return out
 
 
+@_timed
 def axpby(x, y, a, b):
     _chk(x, torch.float32, "x")
     _chk(y, torch.float32, "y")
@@ -323,6 +361,7 @@ def axpby(x, y, a, b):
 
 
 # ------------------------------------------------------------------------------------------------ edge convs
+@_timed
 def im2col_nchw(x, ksize, Kp):
     _chk(x, torch.float32, "x")
     B, C, H, W = x.shape
@@ -332,6 +371,7 @@ def im2col_nchw(x, ksize, Kp):
     return out
 
 
+@_timed
 def final_conv(xa, xb, w, bias):
     """xa: NHWC fp16; xb: NCHW fp32 or None; w: fp32 [Cout,3,3,Ca+Cb] -> NCHW fp32 [B,Cout,H,W]."""
     _chk(xa, ACT_DTYPE, "xa")
@@ -354,6 +394,7 @@ def quantile_ranks(n, q=0.95):
     return int(lo.item()), hi, weight
 
 
+@_timed
 def dynthresh(x_t, pred, objective, alpha, sigma, q=0.95, workspace=None):
     _chk(x_t, torch.float32, "x_t")
     _chk(pred, torch.float32, "pred")
@@ -370,6 +411,7 @@ def dynthresh(x_t, pred, objective, alpha, sigma, q=0.95, workspace=None):
     return s
 
 
+@_timed
 def ddpm_step(x_t, pred, noise, s, objective, sc, *, renoise=None, rn=(0.0, 0.0, 1.0), out=None, x0_out=None):
     """sc: dict of fp32 python floats alpha, sigma, one_minus_c, c, alpha_next, std."""
     _chk(x_t, torch.float32, "x_t")
@@ -384,6 +426,7 @@ def ddpm_step(x_t, pred, noise, s, objective, sc, *, renoise=None, rn=(0.0, 0.0,
     return out
 
 
+@_timed
 def inpaint_blend(img, inpaint, mask, noise, alpha, sigma):
     B, C, H, W = img.shape
     _chk(mask, torch.uint8, "mask")
@@ -393,6 +436,7 @@ def inpaint_blend(img, inpaint, mask, noise, alpha, sigma):
     return img
 
 
+@_timed
 def finalize_image(img, inpaint=None, mask=None):
     B, C, H, W = img.shape
     check(lib().kd_finalize_image(_ptr(img), _ptr(inpaint), _ptr(mask), B, C, H * W, _stream()), "kd_finalize_image")
@@ -400,6 +444,7 @@ def finalize_image(img, inpaint=None, mask=None):
     return img
 
 
+@_timed
 def q_sample(x0, noise, alpha, sigma):
     out = torch.empty_like(x0)
     check(lib().kd_q_sample(_ptr(x0), _ptr(noise), alpha, sigma, _ptr(out), x0.numel(), _stream()), "kd_q_sample")
@@ -407,6 +452,7 @@ def q_sample(x0, noise, alpha, sigma):
     return out
 
 
+@_timed
 def randn(shape, seed, key, device):
     out = torch.empty(shape, device=device, dtype=torch.float32)
     check(lib().kd_randn(_ptr(out), out.numel(), seed & (2**64 - 1), key & (2**64 - 1), _stream()), "kd_randn")
@@ -426,6 +472,7 @@ def neighbour_strips(S, ov, orientation, above=None, side=None, corner=None):
     return view(above, S - ov, 0), view(side, 0, side_x0), view(corner, S - ov, side_x0)
 
 
+@_timed
 def randn_into(out, seed, key):
     assert out.is_contiguous() and out.dtype == torch.float32 and out.is_cuda
     check(lib().kd_randn(_ptr(out), out.numel(), seed & (2**64 - 1), key & (2**64 - 1), _stream()), "kd_randn")
@@ -433,6 +480,7 @@ def randn_into(out, seed, key):
     return out
 
 
+@_timed
 def border_pack(S, overlap_pos, orientation, above, side, corner, device):
     """above / side / corner: None or (tensor_view, channel_stride, row_stride) strips (see neighbour_strips) -> (inpaint, mask)."""
     inpaint = torch.empty((3, S, S), device=device, dtype=torch.float32)

@@ -53,3 +53,20 @@ if os.environ.get("KD_CONV_TABLE"):
         print(f"{label} | {n:3d} | {fl / n / 1e9:8.1f} | {ms / n:7.3f} | {fl / ms / 1e9:7.1f}")
     tot_f, tot_ms = sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values())
     print(f"total conv: {tot_f / 1e12:.3f} TFLOP in {tot_ms:.2f} ms = {tot_f / tot_ms / 1e9:.1f} TFLOP/s")
+
+if os.environ.get("KD_OP_TABLE"):
+    import collections
+
+    ops.op_profile = []
+    run.step(4)
+    torch.cuda.synchronize()
+    prof, ops.op_profile = ops.op_profile, None
+    agg = collections.OrderedDict()
+    for name, e0, e1 in prof:
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+    tot = sum(a[1] for a in agg.values())
+    print(f"op table, B={B}, S={S}: total {tot:.2f} ms ({tot / B:.2f} ms per patch-step)")
+    for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"  {name:16s} n={n:4d}  {ms:8.3f} ms  {100 * ms / tot:5.1f}%")

@@ -71,7 +71,8 @@ def test_conv_gemm_matches_conv2d(cuda_lib, B, H, W, Cin, Cout, k):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(1, 64, 64, 256, 256, 3), (3, 24, 40, 128, 640, 1), (2, 16, 16, 64, 128, 3), (1, 8, 8, 1024, 1024, 3),
-                                               (5, 8, 8, 128, 384, 3), (1, 128, 128, 128, 128, 3)])
+                                               (5, 8, 8, 128, 384, 3), (1, 128, 128, 128, 128, 3), (3, 40, 20, 192, 256, 3),
+                                               (1, 16, 8, 64, 128, 3), (2, 33, 17, 128, 384, 3)])
 def test_conv_pair_kernel_bit_identical_to_single_cta_kernel(cuda_lib, B, H, W, Cin, Cout, k):
     """cta_group::2 persistent kernel vs the single-CTA kernel: same k order per output -> identical bits; odd tile counts,
     N tails (640 = 2.5 x 256) and multi-tile-per-CTA persistence are all exercised."""
@@ -86,11 +87,14 @@ def test_conv_pair_kernel_bit_identical_to_single_cta_kernel(cuda_lib, B, H, W, 
     try:
         ops.set_conv_impl(1)
         ref = ops.conv_gemm(dx, dw, db, ksize=k, act=ops.ACT_SILU, addend=da)
-        ops.set_conv_impl(2)
+        ops.set_conv_impl(4)   # tap-loop CTA-pair kernel: same k order as the single-CTA kernel
         out = ops.conv_gemm(dx, dw, db, ksize=k, act=ops.ACT_SILU, addend=da)
+        ops.set_conv_impl(2)   # halo-reuse variant for 3x3 on >= 16 x 8 images (chunk-major k order: fp32 sums differ in the last bit)
+        out_halo = ops.conv_gemm(dx, dw, db, ksize=k, act=ops.ACT_SILU, addend=da)
         torch.cuda.synchronize()
     finally:
         ops.set_conv_impl(0)
+    assert rel_l2(out_halo, ref) < 2e-4 and float((out_halo.float() - ref.float()).abs().max()) < 2e-2
     assert torch.equal(out, ref)
     err = rel_l2(from_nhwc(out), F.silu(F.conv2d(rb(x), rb(w), b, padding=k // 2)) + rb(add))
     assert err < 5e-3
