@@ -82,6 +82,14 @@ int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
                  const void* addend /* or NULL */, const float* addend_scale /* [B,Cout] or NULL (=1) */, void* out,
                  kd_stream_t stream);
 
+/* kd_conv_gemm that additionally emits fused GroupNorm statistics of the stored output: stats[row][Cout/8] = {sum, sumsq}
+ * (fp32) over 32 output pixels x 8 channels, rows = 4 per 128-pixel M-tile.  kd_conv_stats_layout gives the buffer
+ * geometry for a descriptor (layout[0] = rows, 0 if this shape cannot produce them; [1] = M-tiles per batch group;
+ * [2] = batch images per tile), consumed by kd_oct_reduce. */
+int kd_conv_stats_layout(const KdConvDesc* desc, int* layout /* [3] */);
+int kd_conv_gemm_stats(const KdConvDesc* desc, const void* xa, const void* xb, const void* w, const float* bias, const void* addend,
+                       const float* addend_scale, void* out, float* stats, kd_stream_t stream);
+
 /* ------------------------------------------------------------------ small-M linear (time / conditioning towers, GCA MLP)
  * replaces: nn.Linear on (B, features) tensors: to_time_hiddens, to_time_cond, to_time_tokens, ResnetBlock.time_mlp,
  *           GlobalContext.net, CrossAttention.to_kv on the conditioning tokens.
@@ -109,6 +117,17 @@ int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int
                 const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift, long ss_stride,
                 int Ctot, int act, kd_stream_t stream);
 
+/* Octet-granular statistics (8 channels), the form the conv epilogue emits: any GroupNorm grouping (group sizes are
+ * multiples of 8), including groups that straddle the two sources of a channel concat, is derived from them afterwards.
+ * kd_oct_stats:  partial[b][blk][C/8] = {sum, sumsq} of x over a chunk of pixels (standalone pass, same as kd_gn_stats).
+ * kd_oct_reduce: sums partial rows into out[b][C/8][2]; physical row of (b, i): tile_b = b / TB, sub = b % TB, rpb = rpt / TB,
+ *                row = ((tile_b * tiles + i / rpb) * rpt) + sub * rpb + i % rpb, for i < tiles * rpb  (conv: rpt = 4).
+ * kd_gn_finalize_oct: mean / rstd per (b, group) from the reduced octet sums of one or two sources. */
+int kd_oct_stats(const void* x, int B, long HW, int C, float* partial /* [B][nblk][C/8][2] */, int nblk, kd_stream_t stream);
+int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, int B, int n_oct, float* out /* [B][n_oct][2] */, kd_stream_t stream);
+int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, float scale_a, const float* sum_b, int n_oct_b, float scale_b, int B,
+                       int num_groups, int group_size, double count, float eps, float* mean_rstd, kd_stream_t stream);
+
 /* ------------------------------------------------------------------ K4: GlobalContext gate
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */
 int kd_rowdot(const void* x /* fp16 [B,HW,C] */, const float* w /* [C] */, const float* bias /* [1] or NULL */, float* out /* [B,HW] */,
@@ -116,8 +135,11 @@ int kd_rowdot(const void* x /* fp16 [B,HW,C] */, const float* w /* [C] */, const
 int kd_gca_pool(const void* x, const float* logits, int B, long HW, int C, int nblk, float* part /* [B][nblk][C] */,
                 float* ml /* [B][nblk][2] = {max, sumexp} */, kd_stream_t stream);
 int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled /* [B][C] */, kd_stream_t stream);
-/* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); fp16 in/out */
-int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, int B, long HW, int C, kd_stream_t stream);
+/* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); fp16 in/out.  oct_partial (optional, [B][nblk][C/8][2]):
+ * fused statistics of `out` in kd_oct_stats form, nblk = kd_elementwise_blocks(HW, C). */
+int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, float* oct_partial, int B, long HW, int C,
+                     kd_stream_t stream);
+int kd_elementwise_blocks(long HW, int C);
 
 /* ------------------------------------------------------------------ LayerNorm over channels of NHWC tokens
  * replaces: imagen-pytorch LayerNorm / ChanLayerNorm (gain only, eps 1e-5) and nn.LayerNorm (gain + bias).

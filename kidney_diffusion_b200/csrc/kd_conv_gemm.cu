@@ -33,6 +33,7 @@ struct ConvParams {
   const void* addend;
   const float* addend_scale;
   void* out;
+  float* stats;  // optional per-(row group, channel octet) {sum, sumsq} of the stored output (fused GroupNorm statistics)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -1091,8 +1092,52 @@ extern "C" int kd_set_conv_impl(int impl) {
   return KD_OK;
 }
 
+namespace {
+// tiling the dispatcher will use for `d` (shared by kd_conv_gemm_stats and kd_conv_stats_layout)
+struct Tiling {
+  bool use_pair, use_halo;
+  int TW, TH, TB, tiles_w, tiles_h, tiles_b;
+};
+Tiling choose_tiling(const KdConvDesc* d) {
+  Tiling t;
+  t.use_pair = (g_conv_impl == 2) || (g_conv_impl == 4) || ((g_conv_impl == 0 || g_conv_impl == 3) && d->Cout >= 128);
+  t.use_halo = t.use_pair && g_conv_impl != 4 && g_conv_impl != 3 && d->mode == 0 && d->ksize == 3 && d->H >= HALO_TH &&
+               d->W >= HALO_TW && !d->out_f32 && d->out_mode == 0;
+  if (t.use_halo) {
+    t.TW = HALO_TW; t.TH = HALO_TH; t.TB = 1;
+  } else {
+    t.TH = pow2_ceil(d->H) < 8 ? pow2_ceil(d->H) : 8;
+    const int wmax = BM / t.TH;
+    t.TW = pow2_ceil(d->W) < wmax ? pow2_ceil(d->W) : wmax;
+    t.TB = BM / (t.TH * t.TW);
+  }
+  t.tiles_w = kd_ceil_div(d->W, t.TW);
+  t.tiles_h = kd_ceil_div(d->H, t.TH);
+  t.tiles_b = kd_ceil_div(d->B, t.TB);
+  return t;
+}
+}  // namespace
+
+// layout[0] = total rows of the statistics buffer ([rows][Cout/8][2] fp32), layout[1] = m-tiles per batch group,
+// layout[2] = batch images per tile (TB); 0 rows = this shape does not produce fused statistics
+extern "C" int kd_conv_stats_layout(const KdConvDesc* d, int* layout) {
+  KD_REQUIRE(d && layout, "kd_conv_stats_layout: null argument");
+  const Tiling t = choose_tiling(d);
+  layout[0] = layout[1] = layout[2] = 0;
+  if (!t.use_pair || d->out_f32 || d->out_mode != 0 || t.TB > 2 || d->Cout % 8 != 0) return KD_OK;
+  layout[0] = t.tiles_w * t.tiles_h * t.tiles_b * 4;
+  layout[1] = t.tiles_w * t.tiles_h;
+  layout[2] = t.TB;
+  return KD_OK;
+}
+
 extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
                             const void* addend, const float* addend_scale, void* out, kd_stream_t stream_) {
+  return kd_conv_gemm_stats(d, xa, xb, w, bias, addend, addend_scale, out, nullptr, stream_);
+}
+
+extern "C" int kd_conv_gemm_stats(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
+                                  const void* addend, const float* addend_scale, void* out, float* stats, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(d && xa && w && out, "kd_conv_gemm: null argument");
   KD_REQUIRE(d->mode >= 0 && d->mode <= 2, "kd_conv_gemm: bad mode %d", d->mode);
@@ -1124,7 +1169,7 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
   p.chunks_a = d->Ca / BK;
   p.chunks_per_tap = (d->Ca + d->Cb) / BK;
   p.num_kb = taps * p.chunks_per_tap;
-  p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out;
+  p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out; p.stats = stats;
 
   // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel;
   // 3x3 convolutions on images of at least 16 x 8 pixels use the halo-reuse variant (impl 4 forces the tap-loop pair kernel)
@@ -1164,6 +1209,11 @@ extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb,
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};  // pair kernel: each CTA loads half the tile rows
     rc = encode_map(&mw, w, 2, dims, str, box);
     if (rc) return rc;
+  }
+  if (stats != nullptr) {
+    int lay[3];
+    kd_conv_stats_layout(d, lay);
+    KD_REQUIRE(lay[0] > 0, "kd_conv_gemm_stats: this shape / kernel does not produce fused statistics (see kd_conv_stats_layout)");
   }
   if (use_halo) {
     if (BN == 256) return launch_halo<256, 7>(ma, mb, mw, p, stream);

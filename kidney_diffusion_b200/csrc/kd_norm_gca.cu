@@ -318,7 +318,8 @@ __global__ void gca_finalize_kernel(const float* __restrict__ part, const float*
 }
 
 __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __restrict__ gate, const h16* __restrict__ res,
-                                     h16* __restrict__ out, long HW, int C, int nblk) {
+                                     h16* __restrict__ out, float* __restrict__ oct_partial, long HW, int C, int nblk) {
+  extern __shared__ float sm[];  // [T][2] when statistics are requested
   const int oct = C >> 3;
   const int lanes = blockDim.x / oct;
   const int o = threadIdx.x % oct;
@@ -331,6 +332,7 @@ __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __r
   const long p0 = (long)blockIdx.x * per;
   const long p1 = p0 + per < HW ? p0 + per : HW;
   const long base = (long)b * HW * C + (long)o * 8;
+  float s1 = 0.f, s2 = 0.f;
   for (long p = p0 + pl; p < p1; p += lanes) {
     int4 raw = ld_stream(h + base + p * C);
     float v[8];
@@ -347,6 +349,146 @@ __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __r
     }
     h16x8 o8 = float_to_h16x8(v);
     *reinterpret_cast<int4*>(out + base + p * C) = *reinterpret_cast<int4*>(&o8);
+    if (oct_partial != nullptr) {  // statistics of the rounded values that were stored
+      float f[8];
+      h16x8_to_float(o8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1 += f[j];
+        s2 = fmaf(f[j], f[j], s2);
+      }
+    }
+  }
+  if (oct_partial != nullptr) {
+    sm[threadIdx.x * 2] = s1;
+    sm[threadIdx.x * 2 + 1] = s2;
+    __syncthreads();
+    if (threadIdx.x < oct) {
+      float a1 = 0.f, a2 = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        a1 += sm[(l * oct + threadIdx.x) * 2];
+        a2 += sm[(l * oct + threadIdx.x) * 2 + 1];
+      }
+      float2* dst = reinterpret_cast<float2*>(oct_partial) + ((long)b * nblk + blockIdx.x) * oct + threadIdx.x;
+      *dst = make_float2(a1, a2);
+    }
+  }
+}
+
+// standalone octet statistics (fallback when the producer kernel could not fuse them)
+__global__ void oct_stats_kernel(const h16* __restrict__ x, long HW, int C, float* __restrict__ partial, int nblk) {
+  extern __shared__ float sm[];
+  const int oct = C >> 3;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int b = blockIdx.y;
+  const long per = (HW + nblk - 1) / nblk;
+  const long p0 = (long)blockIdx.x * per;
+  const long p1 = p0 + per < HW ? p0 + per : HW;
+  const h16* xb = x + (long)b * HW * C + (long)o * 8;
+  float s = 0.f, ss = 0.f;
+  long p = p0 + pl;
+  for (; p + 3L * lanes < p1; p += 4L * lanes) {
+    int4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = ld_stream(xb + (p + (long)u * lanes) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      h16x8_to_float(*reinterpret_cast<h16x8*>(&raw[u]), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += v[j];
+        ss = fmaf(v[j], v[j], ss);
+      }
+    }
+  }
+  for (; p < p1; p += lanes) {
+    int4 raw = ld_stream(xb + p * C);
+    float v[8];
+    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s += v[j];
+      ss = fmaf(v[j], v[j], ss);
+    }
+  }
+  sm[threadIdx.x * 2] = s;
+  sm[threadIdx.x * 2 + 1] = ss;
+  __syncthreads();
+  if (threadIdx.x < oct) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      a1 += sm[(l * oct + threadIdx.x) * 2];
+      a2 += sm[(l * oct + threadIdx.x) * 2 + 1];
+    }
+    float2* dst = reinterpret_cast<float2*>(partial) + ((long)b * nblk + blockIdx.x) * oct + threadIdx.x;
+    *dst = make_float2(a1, a2);
+  }
+}
+
+// sum partial rows into out[b][oct]: block = 32 octets x 8 row slices, fixed-order combination
+__global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, int tiles, int TB, int n_oct, float* __restrict__ out) {
+  __shared__ double sred[8][32][2];
+  const int b = blockIdx.y;
+  const int ol = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + ol;
+  const int tile_b = b / TB, sub = b % TB, rpb = rpt / TB;
+  const long count = (long)tiles * rpb;
+  double s1 = 0.0, s2 = 0.0;
+  if (o < n_oct) {
+    const float2* pp = reinterpret_cast<const float2*>(partial);
+    for (long i = sl; i < count; i += 8) {
+      const long row = ((long)tile_b * tiles + i / rpb) * rpt + (long)sub * rpb + i % rpb;
+      const float2 v = pp[row * n_oct + o];
+      s1 += v.x;
+      s2 += v.y;
+    }
+  }
+  sred[sl][ol][0] = s1;
+  sred[sl][ol][1] = s2;
+  __syncthreads();
+  if (sl == 0 && o < n_oct) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int k = 0; k < 8; ++k) {
+      a1 += sred[k][ol][0];
+      a2 += sred[k][ol][1];
+    }
+    reinterpret_cast<float2*>(out)[(long)b * n_oct + o] = make_float2((float)a1, (float)a2);
+  }
+}
+
+// mean / rstd per (b, group) from reduced octet sums of up to two concatenated sources: one warp per group
+__global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, float scale_a, const float* __restrict__ sb, int nb,
+                                       float scale_b, int G, int group_size, double count, float eps, float* __restrict__ mean_rstd) {
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g >= G) return;
+  double s = 0.0, ss = 0.0;
+  for (int o = lane; o < na + nb; o += 32) {
+    if ((o * 8) / group_size != g) continue;
+    if (o < na) {
+      const float2 v = reinterpret_cast<const float2*>(sa)[(long)b * na + o];
+      s += (double)v.x * scale_a;
+      ss += (double)v.y * scale_a * scale_a;
+    } else {
+      const float2 v = reinterpret_cast<const float2*>(sb)[(long)b * nb + (o - na)];
+      s += (double)v.x * scale_b;
+      ss += (double)v.y * scale_b * scale_b;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[((long)b * G + g) * 2] = (float)mean;
+    mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
 
@@ -508,15 +650,50 @@ extern "C" int kd_gca_finalize(const float* part, const float* ml, int B, int nb
   return KD_OK;
 }
 
-extern "C" int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, int B, long HW, int C,
+extern "C" int kd_elementwise_blocks(long HW, int C) {
+  if (C <= 0 || C % 8 != 0 || C / 8 > 256 || HW <= 0) return 0;
+  const int T = threads_for_oct(C / 8);
+  return pick_nblk(HW, T / (C / 8), 1);  // independent of the batch size (batch-invariant reduction order)
+}
+
+extern "C" int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, float* oct_partial, int B, long HW, int C,
                                 kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(h && out && B > 0 && HW > 0, "kd_gate_residual: bad argument");
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
-  const int nblk = pick_nblk(HW, T / (C / 8), B);
-  gate_residual_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const h16*>(h), gate, reinterpret_cast<const h16*>(res),
-                                                        reinterpret_cast<h16*>(out), HW, C, nblk);
+  const int nblk = kd_elementwise_blocks(HW, C);
+  gate_residual_kernel<<<dim3(nblk, B), T, oct_partial ? T * 2 * sizeof(float) : 0, stream>>>(
+      reinterpret_cast<const h16*>(h), gate, reinterpret_cast<const h16*>(res), reinterpret_cast<h16*>(out), oct_partial, HW, C, nblk);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_oct_stats(const void* x, int B, long HW, int C, float* partial, int nblk, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && partial && B > 0 && HW > 0 && nblk > 0, "kd_oct_stats: bad argument");
+  KD_CHECK_OCT(C);
+  const int T = threads_for_oct(C / 8);
+  oct_stats_kernel<<<dim3(nblk, B), T, T * 2 * sizeof(float), stream>>>(reinterpret_cast<const h16*>(x), HW, C, partial, nblk);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, int B, int n_oct, float* out, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(partial && out && rpt > 0 && tiles > 0 && TB > 0 && rpt % TB == 0 && B > 0 && n_oct > 0, "kd_oct_reduce: bad argument");
+  oct_reduce_kernel<<<dim3(kd_ceil_div(n_oct, 32), B), 256, 0, stream>>>(partial, rpt, tiles, TB, n_oct, out);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, float scale_a, const float* sum_b, int n_oct_b, float scale_b, int B,
+                                  int num_groups, int group_size, double count, float eps, float* mean_rstd, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(sum_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && group_size % 8 == 0 && count > 0,
+             "kd_gn_finalize_oct: bad argument");
+  gn_finalize_oct_kernel<<<B, 32 * num_groups, 0, stream>>>(sum_a, n_oct_a, scale_a, sum_b, sum_b ? n_oct_b : 0, scale_b, num_groups,
+                                                            group_size, count, eps, mean_rstd);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

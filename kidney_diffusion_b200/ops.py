@@ -98,8 +98,58 @@ def set_conv_impl(impl):
 
 
 @_timed
+class OctStats:
+    """Per-(row group, channel octet) {sum, sumsq} partials of a tensor + their layout; `reduced()` -> [B, C/8, 2] fp32."""
+
+    def __init__(self, partial, rpt, tiles, TB, B, n_oct):
+        self.partial, self.rpt, self.tiles, self.TB, self.B, self.n_oct = partial, rpt, tiles, TB, B, n_oct
+        self._reduced = None
+
+    def reduced(self):
+        if self._reduced is None:
+            out = torch.empty((self.B, self.n_oct, 2), device=self.partial.device, dtype=torch.float32)
+            check(lib().kd_oct_reduce(_ptr(self.partial), self.rpt, self.tiles, self.TB, self.B, self.n_oct, _ptr(out), _stream()),
+                  "kd_oct_reduce")
+            _count()
+            self._reduced = out
+        return self._reduced
+
+
+@_timed
+def oct_stats(x):
+    """Standalone octet statistics of an NHWC fp16 tensor (used when the producer kernel could not fuse them)."""
+    _chk(x, ACT_DTYPE, "x")
+    B, H, W, C = x.shape
+    nblk = _nblk(H * W, C, B)
+    partial = torch.empty((B, nblk, C // 8, 2), device=x.device, dtype=torch.float32)
+    check(lib().kd_oct_stats(_ptr(x), B, H * W, C, _ptr(partial), nblk, _stream()), "kd_oct_stats")
+    _count()
+    return OctStats(partial, 1, nblk, 1, B, C // 8)
+
+
+def stats_of(x):
+    """Octet statistics attached to `x` by its producer (conv epilogue / gate_residual), else computed standalone; cached."""
+    st = getattr(x, "_kd_stats", None)
+    if st is None:
+        st = oct_stats(x)
+        x._kd_stats = st
+    return st
+
+
+@_timed
+def gn_finalize_oct(stats_a, scale_a, stats_b, scale_b, group_size, num_groups, count, eps=1e-5):
+    sa = stats_a.reduced()
+    sb = stats_b.reduced() if stats_b is not None else None
+    B = stats_a.B
+    mean_rstd = torch.empty((B, num_groups, 2), device=sa.device, dtype=torch.float32)
+    check(lib().kd_gn_finalize_oct(_ptr(sa), stats_a.n_oct, scale_a, _ptr(sb), 0 if stats_b is None else stats_b.n_oct, scale_b, B,
+                                   num_groups, group_size, float(count), eps, _ptr(mean_rstd), _stream()), "kd_gn_finalize_oct")
+    _count()
+    return mean_rstd
+
+
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
-              addend=None, addend_scale=None, out=None):
+              addend=None, addend_scale=None, out=None, want_stats=False):
     """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32)."""
     _chk(xa, ACT_DTYPE, "xa")
     _chk(w, ACT_DTYPE, "w")
@@ -126,10 +176,18 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
         _chk(addend_scale, torch.float32, "addend_scale")
         assert addend_scale.shape == (B, Cout)
     d = KdConvDesc(mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, 1 if out_f32 else 0, addend_f32)
+    stats = None
+    if want_stats:
+        lay = (ctypes.c_int * 3)()
+        check(lib().kd_conv_stats_layout(ctypes.byref(d), lay), "kd_conv_stats_layout")
+        if lay[0] > 0:
+            stats = OctStats(torch.empty((lay[0], Cout // 8, 2), device=xa.device, dtype=torch.float32), 4, lay[1], lay[2], B, Cout // 8)
     with _ConvTimer(2.0 * B * H * W * Cout * taps * (Ca + Cb), (mode, B, H, W, Ca + Cb, Cout, ksize if mode == 0 else 2)):
-        check(lib().kd_conv_gemm(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
-                                 _ptr(out), _stream()), "kd_conv_gemm")
+        check(lib().kd_conv_gemm_stats(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
+                                       _ptr(out), None if stats is None else _ptr(stats.partial), _stream()), "kd_conv_gemm")
     _count()
+    if stats is not None:
+        out._kd_stats = stats
     return out
 
 
@@ -271,12 +329,19 @@ def gca_pool(x, logits):
 
 
 @_timed
-def gate_residual(h, gate, res):
+def gate_residual(h, gate, res, want_stats=False):
     _chk(h, ACT_DTYPE, "h")
     B, H, W, C = h.shape
     out = torch.empty_like(h)
-    check(lib().kd_gate_residual(_ptr(h), _ptr(gate), _ptr(res), _ptr(out), B, H * W, C, _stream()), "kd_gate_residual")
+    stats = None
+    if want_stats:
+        nblk = lib().kd_elementwise_blocks(H * W, C)
+        stats = OctStats(torch.empty((B, nblk, C // 8, 2), device=h.device, dtype=torch.float32), 1, nblk, 1, B, C // 8)
+    check(lib().kd_gate_residual(_ptr(h), _ptr(gate), _ptr(res), _ptr(out), None if stats is None else _ptr(stats.partial), B, H * W, C,
+                                 _stream()), "kd_gate_residual")
     _count()
+    if stats is not None:
+        out._kd_stats = stats
     return out
 
 

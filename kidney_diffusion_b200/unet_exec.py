@@ -298,9 +298,8 @@ class UnetExecutor:
         Cb = xb.shape[3] if exists(xb) else 0
         C = Ca + Cb
         gs = C // G
-        pa = ops.gn_stats(xa, 0, gs, G)
-        pb = ops.gn_stats(xb, Ca, gs, G) if exists(xb) else None
-        mr = ops.gn_finalize(pa, 1.0, pb, b_scale, count=gs * H * W)
+        # statistics come fused from the producer kernel (conv epilogue / gate_residual) when it could emit them
+        mr = ops.gn_finalize_oct(ops.stats_of(xa), 1.0, ops.stats_of(xb) if exists(xb) else None, b_scale, gs, G, count=gs * H * W)
         kw = dict(group_size=gs, num_groups=G, scale_shift=ss, ctot=C)
         ya = ops.gn_apply(xa, mr, gamma, beta, c_offset=0, **kw)
         yb = ops.gn_apply(xb, mr, gamma, beta, c_offset=Ca, src_scale=b_scale, **kw) if exists(xb) else None
@@ -319,7 +318,7 @@ class UnetExecutor:
     def _resnet(self, P, xa, xb, ss_all, c):
         B = xa.shape[0]
         a1, a1b = self._gn(xa, xb, P.b_scale, P.G, P.g1, P.be1, None)
-        h = ops.conv_gemm(a1, P.w1, P.b1, xb=a1b, ksize=3)
+        h = ops.conv_gemm(a1, P.w1, P.b1, xb=a1b, ksize=3, want_stats=not exists(P.xattn))
         if exists(P.xattn):
             h = self._cross_attn(P.xattn, h, c)
         ss = ss_all[:, P.ss_off:P.ss_off + 2 * P.dim_out] if P.ss_off is not None else None
@@ -332,12 +331,12 @@ class UnetExecutor:
             hid = ops.linear_small(pooled, g["w0"], g["b0"], post_act=ops.ACT_SILU)
             gate = ops.linear_small(hid, g["w1"], g["b1"], post_act=ops.ACT_SIGMOID)
             if exists(P.wr):  # out = res_conv(x) + gate * h2, fused in the 1x1 conv epilogue
-                return ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1, addend=h2, addend_scale=gate)
-            return ops.gate_residual(h2, gate, xa)
+                return ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1, addend=h2, addend_scale=gate, want_stats=True)
+            return ops.gate_residual(h2, gate, xa, want_stats=True)
         if exists(P.wr):
             r = ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1)
-            return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=r)
-        return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=xa)
+            return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=r, want_stats=True)
+        return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=xa, want_stats=True)
 
     def _transformer(self, P, x, c):
         B, H, W, C = x.shape
@@ -407,7 +406,7 @@ class UnetExecutor:
         hiddens = []
         for li, d in enumerate(self.downs):
             if exists(d["pre"]):
-                h = ops.conv_gemm(h, d["pre"][0], d["pre"][1], mode=1)
+                h = ops.conv_gemm(h, d["pre"][0], d["pre"][1], mode=1, want_stats=True)
             h = self._resnet(d["init"], h, None, ss_all, c)
             for P in d["blocks"]:
                 h = self._resnet(P, h, None, ss_all, None)
@@ -416,9 +415,9 @@ class UnetExecutor:
                 h = self._transformer(d["attn"], h, c)
             hiddens.append(h)
             if exists(d["post"]):
-                h = ops.conv_gemm(h, d["post"][0], d["post"][1], mode=1)
+                h = ops.conv_gemm(h, d["post"][0], d["post"][1], mode=1, want_stats=True)
             elif exists(d["post_parallel"]):
-                h = ops.conv_gemm(h, d["post_parallel"][0], d["post_parallel"][1], ksize=3)
+                h = ops.conv_gemm(h, d["post_parallel"][0], d["post_parallel"][1], ksize=3, want_stats=True)
             if taps is not None:
                 taps[f"down{li}"] = h
 

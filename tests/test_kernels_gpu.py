@@ -513,3 +513,42 @@ def test_border_pack_matches_reference_layout(cuda_lib, orientation):
         cont = lambda st: None if st is None else (st[0].contiguous(), st[0].shape[1] * st[0].shape[2], st[0].shape[2])
         op2, om2 = ops.border_pack(S, ov, orientation, cont(sa), cont(ss), cont(sc), DEV)
         assert torch.equal(op2.cpu(), ip) and torch.equal(om2.cpu().float(), im)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,mode", [(2, 32, 32, 128, 128, 3, 0), (3, 8, 8, 128, 256, 3, 0), (1, 40, 24, 64, 384, 1, 0), (2, 32, 32, 64, 128, 2, 1),
+                                                  (1, 128, 64, 128, 128, 3, 0)])
+def test_fused_groupnorm_statistics_match_standalone(cuda_lib, B, H, W, Cin, Cout, k, mode):
+    """Octet statistics emitted by the conv epilogue (tap-loop and halo kernels, TB = 1 and 2, partial tiles) == a standalone
+    pass over the stored tensor == exact fp64 sums of the stored values."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(H + Cout)
+    Hin, Win = (2 * H, 2 * W) if mode == 1 else (H, W)
+    taps = 4 if mode == 1 else k * k
+    x = torch.randn(B, Cin, Hin, Win, generator=g)
+    w = bf(torch.randn(Cout, taps * Cin, generator=g) / math.sqrt(taps * Cin)).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    out = ops.conv_gemm(nhwc(x), w, b, mode=mode, ksize=k, want_stats=True)
+    st = getattr(out, "_kd_stats", None)
+    assert st is not None
+    fused = st.reduced().double().cpu()
+    alone = ops.oct_stats(out).reduced().double().cpu()
+    o = out.double().cpu().view(B, H * W, Cout // 8, 8)
+    exact = torch.stack((o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))), dim=-1)
+    for name, got in (("fused", fused), ("standalone", alone)):
+        err = float(((got - exact).abs() / (exact.abs() + 1.0)).max())
+        print(f"{name} octet statistics max rel err {err:.2e}")
+        assert err < 2e-5
+    # gate_residual epilogue statistics
+    gate = torch.rand(B, Cout, generator=g).to(DEV)
+    res = bf(torch.randn(B, H, W, Cout, generator=g)).to(DEV)
+    o2 = ops.gate_residual(out, gate, res, want_stats=True)
+    got = o2._kd_stats.reduced().double().cpu()
+    oo = o2.double().cpu().view(B, H * W, Cout // 8, 8)
+    exact2 = torch.stack((oo.sum(dim=(1, 3)), (oo * oo).sum(dim=(1, 3))), dim=-1)
+    assert float(((got - exact2).abs() / (exact2.abs() + 1.0)).max()) < 2e-5
+    # finalize from octets == GroupNorm statistics of the stored tensor
+    mr = ops.gn_finalize_oct(st, 1.0, None, 1.0, Cout // 8, 8, count=(Cout // 8) * H * W).cpu()
+    of = out.float().cpu().permute(0, 3, 1, 2).reshape(B, 8, -1)
+    assert torch.allclose(mr[..., 0], of.mean(-1), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(mr[..., 1], (of.var(-1, unbiased=False) + 1e-5).rsqrt(), atol=1e-3, rtol=1e-3)
