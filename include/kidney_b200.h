@@ -120,13 +120,15 @@ int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int
 /* Octet-granular statistics (8 channels), the form the conv epilogue emits: any GroupNorm grouping (group sizes are
  * multiples of 8), including groups that straddle the two sources of a channel concat, is derived from them afterwards.
  * kd_oct_stats:  partial[b][blk][C/8] = {sum, sumsq} of x over a chunk of pixels (standalone pass, same as kd_gn_stats).
- * kd_oct_reduce: sums partial rows into out[b][C/8][2]; physical row of (b, i): tile_b = b / TB, sub = b % TB, rpb = rpt / TB,
+ * kd_oct_reduce: first-level sum of partial rows into out[b][NS][C/8][2], NS = kd_oct_reduce_splits(rpt, tiles, TB); physical
+ *                row of logical (b, i): tile_b = b / TB, sub = b % TB, rpb = rpt / TB,
  *                row = ((tile_b * tiles + i / rpb) * rpt) + sub * rpb + i % rpb, for i < tiles * rpb  (conv: rpt = 4).
- * kd_gn_finalize_oct: mean / rstd per (b, group) from the reduced octet sums of one or two sources. */
+ * kd_gn_finalize_oct: mean / rstd per (b, group) from the split sums of one or two (concatenated) sources. */
 int kd_oct_stats(const void* x, int B, long HW, int C, float* partial /* [B][nblk][C/8][2] */, int nblk, kd_stream_t stream);
-int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, int B, int n_oct, float* out /* [B][n_oct][2] */, kd_stream_t stream);
-int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, float scale_a, const float* sum_b, int n_oct_b, float scale_b, int B,
-                       int num_groups, int group_size, double count, float eps, float* mean_rstd, kd_stream_t stream);
+int kd_oct_reduce_splits(int rpt, int tiles, int TB);
+int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, int B, int n_oct, float* out /* [B][NS][n_oct][2] */, kd_stream_t stream);
+int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, float scale_a, const float* sum_b, int n_oct_b, int ns_b, float scale_b,
+                       int B, int num_groups, int group_size, double count, float eps, float* mean_rstd, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ K4: GlobalContext gate
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */

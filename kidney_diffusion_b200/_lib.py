@@ -50,7 +50,8 @@ SIGNATURES = {
     "kd_elementwise_blocks": (c_int, [_L, _I]),
     "kd_oct_stats": (c_int, [_P, _I, _L, _I, _P, _I, _P]),
     "kd_oct_reduce": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
-    "kd_gn_finalize_oct": (c_int, [_P, _I, _F, _P, _I, _F, _I, _I, _I, c_double, _F, _P, _P]),
+    "kd_oct_reduce_splits": (c_int, [_I, _I, _I]),
+    "kd_gn_finalize_oct": (c_int, [_P, _I, _I, _F, _P, _I, _I, _F, _I, _I, _I, c_double, _F, _P, _P]),
     "kd_layernorm_h16": (c_int, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_layernorm_f32": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_kv_assemble": (c_int, [_P, _L, _I, _P, _I, _P, _P, _I, _I, _P]),

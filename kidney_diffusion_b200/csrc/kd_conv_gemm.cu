@@ -593,6 +593,10 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] += a[j];
             }
+            if (!row_ok) {  // rows outside the image are clipped by the TMA store; zeros keep the fused statistics exact
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            }
             const uint32_t chunk16 = (uint32_t)(half * 4 + q);
             const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
             const h16x8 o8 = float_to_h16x8(v);
@@ -612,6 +616,36 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
             }
           }
           tma_store_commit();
+        }
+        if (p.stats != nullptr && tile_in_range) {
+          // fused GroupNorm statistics: per warp (32 rows) and channel octet, {sum, sumsq} of the ROUNDED values just
+          // staged (exactly what a separate pass over the stored tensor would see); fixed order -> deterministic.
+          // lane -> (octet = lane & 7, 8-row slice = lane >> 3); the 4 slices of a warp are merged by two shuffles.
+          const int o = lane & 7, sl = lane >> 3;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t row = (uint32_t)(quarter * 32 + sl * 8 + i);
+            const uint32_t src = stage + row * 128u + (((uint32_t)o ^ (row & 7u)) << 4);
+            int4 raw;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(src));
+            float f[8];
+            h16x8_to_float(*reinterpret_cast<const h16x8*>(&raw), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s1 += f[j];
+              s2 = fmaf(f[j], f[j], s2);
+            }
+          }
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (sl == 0 && nc0 + o * 8 < p.Cout) {
+            const long long m_tile_lin = ((long long)tile_b * p.tiles_h + tile_h) * p.tiles_w + tile_w;
+            float2* dstp = reinterpret_cast<float2*>(p.stats) + (m_tile_lin * 4 + quarter) * (p.Cout >> 3) + ((nc0 >> 3) + o);
+            *dstp = make_float2(s1, s2);
+          }
         }
       }
     }

@@ -428,40 +428,43 @@ __global__ void oct_stats_kernel(const h16* __restrict__ x, long HW, int C, floa
   }
 }
 
-// sum partial rows into out[b][oct]: block = 32 octets x 8 row slices, fixed-order combination
-__global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, int tiles, int TB, int n_oct, float* __restrict__ out) {
-  __shared__ double sred[8][32][2];
-  const int b = blockIdx.y;
-  const int ol = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int o = blockIdx.x * 32 + ol;
+// first-level reduction of partial rows: grid (NS splits, B); each block sums a contiguous range of the logical rows of its
+// batch image for all octets (thread = fixed octet, `lanes` threads per octet) -> out[b][split][oct]; fixed order throughout
+__global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, int tiles, int TB, int n_oct, int NS,
+                                  float* __restrict__ out) {
+  extern __shared__ double sred[];  // [T][2]
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int o = threadIdx.x % n_oct, l = threadIdx.x / n_oct;
+  const int lanes = blockDim.x / n_oct;
   const int tile_b = b / TB, sub = b % TB, rpb = rpt / TB;
   const long count = (long)tiles * rpb;
+  const long per = (count + NS - 1) / NS;
+  const long r0 = (long)sp * per, r1 = (r0 + per < count) ? r0 + per : count;
   double s1 = 0.0, s2 = 0.0;
-  if (o < n_oct) {
-    const float2* pp = reinterpret_cast<const float2*>(partial);
-    for (long i = sl; i < count; i += 8) {
-      const long row = ((long)tile_b * tiles + i / rpb) * rpt + (long)sub * rpb + i % rpb;
-      const float2 v = pp[row * n_oct + o];
-      s1 += v.x;
-      s2 += v.y;
-    }
+  const float2* pp = reinterpret_cast<const float2*>(partial);
+  for (long i = r0 + l; i < r1; i += lanes) {
+    const long row = ((long)tile_b * tiles + i / rpb) * rpt + (long)sub * rpb + i % rpb;
+    const float2 v = pp[row * n_oct + o];
+    s1 += v.x;
+    s2 += v.y;
   }
-  sred[sl][ol][0] = s1;
-  sred[sl][ol][1] = s2;
+  sred[threadIdx.x * 2] = s1;
+  sred[threadIdx.x * 2 + 1] = s2;
   __syncthreads();
-  if (sl == 0 && o < n_oct) {
+  if (threadIdx.x < n_oct) {
     double a1 = 0.0, a2 = 0.0;
-    for (int k = 0; k < 8; ++k) {
-      a1 += sred[k][ol][0];
-      a2 += sred[k][ol][1];
+    for (int k = 0; k < lanes; ++k) {
+      a1 += sred[(k * n_oct + threadIdx.x) * 2];
+      a2 += sred[(k * n_oct + threadIdx.x) * 2 + 1];
     }
-    reinterpret_cast<float2*>(out)[(long)b * n_oct + o] = make_float2((float)a1, (float)a2);
+    reinterpret_cast<float2*>(out)[((long)b * NS + sp) * n_oct + threadIdx.x] = make_float2((float)a1, (float)a2);
   }
 }
 
 // mean / rstd per (b, group) from reduced octet sums of up to two concatenated sources: one warp per group
-__global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, float scale_a, const float* __restrict__ sb, int nb,
-                                       float scale_b, int G, int group_size, double count, float eps, float* __restrict__ mean_rstd) {
+__global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int nsa, float scale_a, const float* __restrict__ sb, int nb,
+                                       int nsb, float scale_b, int G, int group_size, double count, float eps,
+                                       float* __restrict__ mean_rstd) {
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
@@ -469,13 +472,17 @@ __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, flo
   for (int o = lane; o < na + nb; o += 32) {
     if ((o * 8) / group_size != g) continue;
     if (o < na) {
-      const float2 v = reinterpret_cast<const float2*>(sa)[(long)b * na + o];
-      s += (double)v.x * scale_a;
-      ss += (double)v.y * scale_a * scale_a;
+      for (int k = 0; k < nsa; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(sa)[((long)b * nsa + k) * na + o];
+        s += (double)v.x * scale_a;
+        ss += (double)v.y * scale_a * scale_a;
+      }
     } else {
-      const float2 v = reinterpret_cast<const float2*>(sb)[(long)b * nb + (o - na)];
-      s += (double)v.x * scale_b;
-      ss += (double)v.y * scale_b * scale_b;
+      for (int k = 0; k < nsb; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(sb)[((long)b * nsb + k) * nb + (o - na)];
+        s += (double)v.x * scale_b;
+        ss += (double)v.y * scale_b * scale_b;
+      }
     }
   }
 #pragma unroll
@@ -679,21 +686,34 @@ extern "C" int kd_oct_stats(const void* x, int B, long HW, int C, float* partial
   return KD_OK;
 }
 
+extern "C" int kd_oct_reduce_splits(int rpt, int tiles, int TB) {
+  if (rpt <= 0 || tiles <= 0 || TB <= 0) return 0;
+  const long count = (long)tiles * (rpt / TB);
+  long ns = count / 32;
+  if (ns < 1) ns = 1;
+  if (ns > 64) ns = 64;
+  return (int)ns;
+}
+
 extern "C" int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, int B, int n_oct, float* out, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(partial && out && rpt > 0 && tiles > 0 && TB > 0 && rpt % TB == 0 && B > 0 && n_oct > 0, "kd_oct_reduce: bad argument");
-  oct_reduce_kernel<<<dim3(kd_ceil_div(n_oct, 32), B), 256, 0, stream>>>(partial, rpt, tiles, TB, n_oct, out);
+  KD_REQUIRE(partial && out && rpt > 0 && tiles > 0 && TB > 0 && rpt % TB == 0 && B > 0 && n_oct > 0 && n_oct <= 256,
+             "kd_oct_reduce: bad argument");
+  const int NS = kd_oct_reduce_splits(rpt, tiles, TB);
+  const int T = threads_for_oct(n_oct);
+  oct_reduce_kernel<<<dim3(NS, B), T, T * 2 * sizeof(double), stream>>>(partial, rpt, tiles, TB, n_oct, NS, out);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
 
-extern "C" int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, float scale_a, const float* sum_b, int n_oct_b, float scale_b, int B,
-                                  int num_groups, int group_size, double count, float eps, float* mean_rstd, kd_stream_t stream_) {
+extern "C" int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, float scale_a, const float* sum_b, int n_oct_b, int ns_b,
+                                  float scale_b, int B, int num_groups, int group_size, double count, float eps, float* mean_rstd,
+                                  kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(sum_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && group_size % 8 == 0 && count > 0,
+  KD_REQUIRE(sum_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && group_size % 8 == 0 && count > 0 && ns_a > 0,
              "kd_gn_finalize_oct: bad argument");
-  gn_finalize_oct_kernel<<<B, 32 * num_groups, 0, stream>>>(sum_a, n_oct_a, scale_a, sum_b, sum_b ? n_oct_b : 0, scale_b, num_groups,
-                                                            group_size, count, eps, mean_rstd);
+  gn_finalize_oct_kernel<<<B, 32 * num_groups, 0, stream>>>(sum_a, n_oct_a, ns_a, scale_a, sum_b, sum_b ? n_oct_b : 0, sum_b ? ns_b : 0,
+                                                            scale_b, num_groups, group_size, count, eps, mean_rstd);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -97,7 +97,6 @@ def set_conv_impl(impl):
     check(lib().kd_set_conv_impl(int(impl)), "kd_set_conv_impl")
 
 
-@_timed
 class OctStats:
     """Per-(row group, channel octet) {sum, sumsq} partials of a tensor + their layout; `reduced()` -> [B, C/8, 2] fp32."""
 
@@ -106,8 +105,10 @@ class OctStats:
         self._reduced = None
 
     def reduced(self):
+        """[B, NS, C/8, 2] split sums (NS <= 64 row ranges per image; kd_gn_finalize_oct adds them in fixed order)."""
         if self._reduced is None:
-            out = torch.empty((self.B, self.n_oct, 2), device=self.partial.device, dtype=torch.float32)
+            self.ns = lib().kd_oct_reduce_splits(self.rpt, self.tiles, self.TB)
+            out = torch.empty((self.B, self.ns, self.n_oct, 2), device=self.partial.device, dtype=torch.float32)
             check(lib().kd_oct_reduce(_ptr(self.partial), self.rpt, self.tiles, self.TB, self.B, self.n_oct, _ptr(out), _stream()),
                   "kd_oct_reduce")
             _count()
@@ -127,12 +128,18 @@ def oct_stats(x):
     return OctStats(partial, 1, nblk, 1, B, C // 8)
 
 
+FUSED_STATS = True  # debugging switch: False forces the standalone statistics pass
+
+
 def stats_of(x):
     """Octet statistics attached to `x` by its producer (conv epilogue / gate_residual), else computed standalone; cached."""
-    st = getattr(x, "_kd_stats", None)
+    st = getattr(x, "_kd_stats", None) if FUSED_STATS else getattr(x, "_kd_stats_alone", None)
     if st is None:
         st = oct_stats(x)
-        x._kd_stats = st
+        if FUSED_STATS:
+            x._kd_stats = st
+        else:
+            x._kd_stats_alone = st
     return st
 
 
@@ -142,12 +149,14 @@ def gn_finalize_oct(stats_a, scale_a, stats_b, scale_b, group_size, num_groups, 
     sb = stats_b.reduced() if stats_b is not None else None
     B = stats_a.B
     mean_rstd = torch.empty((B, num_groups, 2), device=sa.device, dtype=torch.float32)
-    check(lib().kd_gn_finalize_oct(_ptr(sa), stats_a.n_oct, scale_a, _ptr(sb), 0 if stats_b is None else stats_b.n_oct, scale_b, B,
-                                   num_groups, group_size, float(count), eps, _ptr(mean_rstd), _stream()), "kd_gn_finalize_oct")
+    check(lib().kd_gn_finalize_oct(_ptr(sa), stats_a.n_oct, stats_a.ns, scale_a, _ptr(sb), 0 if stats_b is None else stats_b.n_oct,
+                                   0 if stats_b is None else stats_b.ns, scale_b, B, num_groups, group_size, float(count), eps,
+                                   _ptr(mean_rstd), _stream()), "kd_gn_finalize_oct")
     _count()
     return mean_rstd
 
 
+@_timed
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
               addend=None, addend_scale=None, out=None, want_stats=False):
     """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32)."""

@@ -531,8 +531,8 @@ def test_fused_groupnorm_statistics_match_standalone(cuda_lib, B, H, W, Cin, Cou
     out = ops.conv_gemm(nhwc(x), w, b, mode=mode, ksize=k, want_stats=True)
     st = getattr(out, "_kd_stats", None)
     assert st is not None
-    fused = st.reduced().double().cpu()
-    alone = ops.oct_stats(out).reduced().double().cpu()
+    fused = st.reduced().double().cpu().sum(1)
+    alone = ops.oct_stats(out).reduced().double().cpu().sum(1)
     o = out.double().cpu().view(B, H * W, Cout // 8, 8)
     exact = torch.stack((o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))), dim=-1)
     for name, got in (("fused", fused), ("standalone", alone)):
@@ -543,7 +543,7 @@ def test_fused_groupnorm_statistics_match_standalone(cuda_lib, B, H, W, Cin, Cou
     gate = torch.rand(B, Cout, generator=g).to(DEV)
     res = bf(torch.randn(B, H, W, Cout, generator=g)).to(DEV)
     o2 = ops.gate_residual(out, gate, res, want_stats=True)
-    got = o2._kd_stats.reduced().double().cpu()
+    got = o2._kd_stats.reduced().double().cpu().sum(1)
     oo = o2.double().cpu().view(B, H * W, Cout // 8, 8)
     exact2 = torch.stack((oo.sum(dim=(1, 3)), (oo * oo).sum(dim=(1, 3))), dim=-1)
     assert float(((got - exact2).abs() / (exact2.abs() + 1.0)).max()) < 2e-5
