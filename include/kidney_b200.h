@@ -172,6 +172,13 @@ int kd_axpby(const float* x, const float* y, float a, float b, float* out, long 
  *           and Unet.final_conv (3x3, Cout = 3) on cat(x, lowres_cond_img). */
 int kd_im2col_nchw(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int W, int ksize, void* out /* fp16 [B*H*W, Kp] */,
                    int Kp, kd_stream_t stream);
+/* CrossEmbedLayer without a panel, for <= 3 image channels per call and Cout in {64, 128}: tcgen05 implicit GEMM over
+ * element-shifted halo rows kept in shared memory (see csrc/kd_init_conv.cu).  w_packed: fp16 [Cout][Kp], Kp =
+ * kd_init_conv_kp(C, ksize), column (ky*C + c)*16 + kx holds the merged ksize x ksize filter tap (ky, kx) of channel c
+ * (kx >= ksize: zero).  out = conv + bias + addend (addend: fp16 NHWC or NULL; more channels = chained calls). */
+int kd_init_conv_kp(int C, int ksize);
+int kd_init_conv(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int W, int ksize, const void* w_packed, const float* bias,
+                 const void* addend, void* out /* fp16 [B,H,W,Cout] */, int Cout, kd_stream_t stream);
 int kd_final_conv(const void* xa /* fp16 [B,H,W,Ca] */, int Ca, const float* xb /* fp32 NCHW [B,Cb,H,W] or NULL */, int Cb,
                   const float* w /* fp32 [Cout][3][3][Ca+Cb] */, const float* bias, float* out /* fp32 NCHW [B,Cout,H,W] */, int B,
                   int H, int W, int Cout, kd_stream_t stream);

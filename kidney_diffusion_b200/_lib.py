@@ -59,6 +59,8 @@ SIGNATURES = {
     "kd_attn_cross": (c_int, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "kd_attn_small_f32": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "kd_axpby": (c_int, [_P, _P, _F, _F, _P, _L, _P]),
+    "kd_init_conv_kp": (c_int, [_I, _I]),
+    "kd_init_conv": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "kd_im2col_nchw": (c_int, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "kd_final_conv": (c_int, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "kd_dynthresh_workspace_bytes": (c_size_t, [_I]),

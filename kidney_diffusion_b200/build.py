@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkidney_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 
-SOURCES = ["kd_abi.cu", "kd_conv_gemm.cu", "kd_norm_gca.cu", "kd_cond_attn.cu", "kd_sampler.cu", "kd_edge_convs.cu", "kd_experiments.cu"]
+SOURCES = ["kd_abi.cu", "kd_conv_gemm.cu", "kd_norm_gca.cu", "kd_cond_attn.cu", "kd_sampler.cu", "kd_edge_convs.cu", "kd_init_conv.cu", "kd_experiments.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

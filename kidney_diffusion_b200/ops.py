@@ -445,6 +445,32 @@ def im2col_nchw(x, ksize, Kp):
     return out
 
 
+def init_conv_kp(C, ksize):
+    return lib().kd_init_conv_kp(C, ksize)
+
+
+@_timed
+def init_conv(x, ksize, w_packed, bias, addend, out, algo_taps=None):
+    """CrossEmbedLayer slice for <= 3 channels: out (NHWC fp16) = conv_ks(x NCHW fp32) + bias + addend.
+    algo_taps: un-merged taps per (input channel, output channel) for the algorithmic FLOP count."""
+    _chk(x, torch.float32, "x")
+    _chk(w_packed, ACT_DTYPE, "w_packed")
+    _chk(out, ACT_DTYPE, "out")
+    B, C, H, W = x.shape
+    Cout = out.shape[-1]
+    assert w_packed.shape == (Cout, init_conv_kp(C, ksize)), (w_packed.shape, Cout, C, ksize)
+    if addend is not None:
+        _chk(addend, ACT_DTYPE, "addend")
+        assert addend.shape == out.shape
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    with _ConvTimer(2.0 * B * H * W * Cout * C * (algo_taps if algo_taps is not None else ksize * ksize), (3, B, H, W, C, Cout, ksize)):
+        check(lib().kd_init_conv(_ptr(x), B, C, H, W, ksize, _ptr(w_packed), _ptr(bias), _ptr(addend), _ptr(out), Cout, _stream()),
+              "kd_init_conv")
+    _count()
+    return out
+
+
 @_timed
 def final_conv(xa, xb, w, bias):
     """xa: NHWC fp16; xb: NCHW fp32 or None; w: fp32 [Cout,3,3,Ca+Cb] -> NCHW fp32 [B,Cout,H,W]."""

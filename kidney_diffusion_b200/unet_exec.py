@@ -133,11 +133,31 @@ class UnetExecutor:
             return _bf(W), Kp
 
         self.init_wx, self.init_kpx = pack_panel_w(x_idx)
+
+        # panel-free path (ops.init_conv): <= 3 image channels per call, K ordered (ky, c, kx padded to 16)
+        self.init_direct = self.dim in (64, 128)
+
+        def pack_direct_w(idx):
+            groups = []
+            for g0 in range(0, len(idx), 3):
+                sub = idx[g0:g0 + 3]
+                Wd = torch.zeros(self.dim, ks, len(sub), 16, device=device)
+                Wd[..., :ks] = Wm[..., sub].permute(0, 1, 3, 2)  # [n, ky, kx, c] -> [n, ky, c, kx]
+                Kp = ops.init_conv_kp(len(sub), ks)
+                W = torch.zeros(self.dim, Kp, device=device)
+                W[:, :ks * len(sub) * 16] = Wd.reshape(self.dim, -1)
+                groups.append((g0, g0 + len(sub), _bf(W)))
+            return groups
+
+        if self.init_direct:
+            self.init_dx = pack_direct_w(x_idx)
         # algorithmic (un-merged, un-padded) K per input channel, averaged over output channels: sum_k k^2 * cout_k / dim
         self.init_algo_k = sum(c.kernel_size[0] ** 2 * c.out_channels for c in u.init_conv.convs) / self.dim
         self.n_fixed = len(fixed_idx)
         if self.n_fixed:
             self.init_wf, self.init_kpf = pack_panel_w(fixed_idx)
+            if self.init_direct:
+                self.init_df = pack_direct_w(fixed_idx)
 
         # ---- conditioning towers
         self.Tc, self.cd = u.time_cond_dim, u.cond_dim
@@ -278,10 +298,17 @@ class UnetExecutor:
             if "init_base" not in st:
                 st["init_base"] = torch.empty((B, S, S, self.dim), device=fixed.device, dtype=BF16)
             self.init_base = st["init_base"]
-            self._init_gemm(fixed, self.init_wf, self.init_kpf, None, None, self.init_base)
+            self._init_gemm(fixed, self.init_wf, self.init_kpf, None, None, self.init_base, getattr(self, "init_df", None))
 
-    def _init_gemm(self, img, w, Kp, bias, addend, out):
+    def _init_gemm(self, img, w, Kp, bias, addend, out, direct):
         B, _, S, S2 = img.shape
+        if self.init_direct:
+            # chained <= 3-channel slices: out = conv(slice_0) + bias + addend, then out = conv(slice_i) + out
+            for i, (c0, c1, wd) in enumerate(direct):
+                sub = img if (c0 == 0 and c1 == img.shape[1]) else img[:, c0:c1].contiguous()
+                ops.init_conv(sub, self.init_ks, wd, bias if i == 0 else None, addend if i == 0 else out, out,
+                              algo_taps=self.init_algo_k)
+            return
         per = S * S2 * Kp * 2
         chunk = max(1, min(B, IM2COL_BUDGET_BYTES // per))
         for b0 in range(0, B, chunk):
@@ -394,7 +421,7 @@ class UnetExecutor:
 
         # --- init conv (per-step part: the 3 image channels of x; fixed part added in the epilogue)
         h = torch.empty((B, S, S2, self.dim), device=dev, dtype=BF16)
-        self._init_gemm(x, self.init_wx, self.init_kpx, self.init_bias, self.init_base, h)
+        self._init_gemm(x, self.init_wx, self.init_kpx, self.init_bias, self.init_base, h, getattr(self, "init_dx", None))
         if taps is not None:
             taps["init_conv"] = h
         init_residual = h if u.init_conv_to_final_conv_residual else None

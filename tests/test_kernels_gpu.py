@@ -371,6 +371,45 @@ def test_im2col_and_cross_embed(cuda_lib):
     assert err < 5e-3
 
 
+INIT_CASES = [
+    # B, C, H, W, ks, Cout, addend
+    (1, 3, 32, 32, 15, 128, False),
+    (2, 3, 70, 200, 15, 128, True),     # two column strips, partial strip, odd row count -> single-row last pass
+    (1, 1, 33, 129, 7, 64, True),       # one column past the strip boundary
+    (3, 2, 16, 16, 3, 64, False),
+    (1, 3, 256, 256, 15, 128, True),    # several row segments per strip: ring re-primed per work unit
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,ks,Cout,use_add", INIT_CASES)
+def test_init_conv_panel_free(cuda_lib, B, C, H, W, ks, Cout, use_add):
+    """kd_init_conv (shifted-copy halo rows + SWIZZLE_NONE UMMA) against F.conv2d on the fp16-rounded operands."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 1000 + H + W + ks)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Cout, C, ks, ks, generator=g) / math.sqrt(C * ks * ks)
+    bias = torch.randn(Cout, generator=g)
+    add = torch.randn(B, H, W, Cout, generator=g) if use_add else None
+    Kp = ops.init_conv_kp(C, ks)
+    wp = torch.zeros(Cout, ks, C, 16)
+    wp[..., :ks] = w.permute(0, 2, 1, 3)  # [n, c, ky, kx] -> [n, ky, c, kx]
+    W2 = torch.zeros(Cout, Kp)
+    W2[:, :ks * C * 16] = wp.reshape(Cout, -1)
+    out = torch.empty(B, H, W, Cout, device=DEV, dtype=torch.float16)
+    ops.init_conv(x.to(DEV), ks, bf(W2).to(DEV), bias.to(DEV), None if add is None else bf(add).to(DEV), out)
+    ref = F.conv2d(rb(x), rb(w), bias, padding=ks // 2)
+    if add is not None:
+        ref = ref + rb(add).permute(0, 3, 1, 2)
+    got = from_nhwc(out)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < 2e-3, rel_l2(got, ref)
+    # chained in-place accumulation (addend aliases out), as the executor uses for > 3 fixed channels
+    ops.init_conv(x.to(DEV), ks, bf(W2).to(DEV), None, out, out)
+    ref2 = rb(ref) + F.conv2d(rb(x), rb(w), None, padding=ks // 2)
+    assert rel_l2(from_nhwc(out), ref2) < 2e-3
+
+
 def test_final_conv(cuda_lib):
     from kidney_diffusion_b200 import ops
 
