@@ -82,13 +82,18 @@ int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
                  const void* addend /* or NULL */, const float* addend_scale /* [B,Cout] or NULL (=1) */, void* out,
                  kd_stream_t stream);
 
-/* kd_conv_gemm that additionally emits fused GroupNorm statistics of the stored output: stats[row][Cout/8] = {sum, sumsq}
- * (fp32) over 32 output pixels x 8 channels, rows = 4 per 128-pixel M-tile.  kd_conv_stats_layout gives the buffer
- * geometry for a descriptor (layout[0] = rows, 0 if this shape cannot produce them; [1] = M-tiles per batch group;
- * [2] = batch images per tile), consumed by kd_oct_reduce. */
+/* kd_conv_gemm whose epilogue additionally emits, for the consumers of the stored output,
+ *   stats      : fused GroupNorm statistics, stats[row][Cout/8] = {sum, sumsq} (fp32) over 32 output pixels x 8 channels,
+ *                rows = 4 per 128-pixel M-tile.  kd_conv_stats_layout gives the buffer geometry for a descriptor (layout[0] =
+ *                rows, 0 if this shape cannot produce fused outputs; [1] = M-tiles per batch group; [2] = batch images per
+ *                tile), consumed by kd_oct_reduce;
+ *   logit_parts: the GlobalContext to_k 1x1 conv (replaces kd_rowdot): logit_parts[g][b*H*W + n] = sum over the 64 output
+ *                channels of group g of out[b,n,c] * logit_w[c]; kd_gca_pool adds the Cout/64 parts in fixed order.
+ * Either may be NULL; both need layout[0] > 0; logits also need out_mode 0, Cout % 64 == 0 and no addend_scale. */
 int kd_conv_stats_layout(const KdConvDesc* desc, int* layout /* [3] */);
-int kd_conv_gemm_stats(const KdConvDesc* desc, const void* xa, const void* xb, const void* w, const float* bias, const void* addend,
-                       const float* addend_scale, void* out, float* stats, kd_stream_t stream);
+int kd_conv_gemm_fused(const KdConvDesc* desc, const void* xa, const void* xb, const void* w, const float* bias, const void* addend,
+                       const float* addend_scale, void* out, float* stats, const float* logit_w, float* logit_parts,
+                       kd_stream_t stream);
 
 /* ------------------------------------------------------------------ small-M linear (time / conditioning towers, GCA MLP)
  * replaces: nn.Linear on (B, features) tensors: to_time_hiddens, to_time_cond, to_time_tokens, ResnetBlock.time_mlp,
@@ -134,8 +139,8 @@ int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, float scale_a,
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */
 int kd_rowdot(const void* x /* fp16 [B,HW,C] */, const float* w /* [C] */, const float* bias /* [1] or NULL */, float* out /* [B,HW] */,
               int B, long HW, int C, kd_stream_t stream);
-int kd_gca_pool(const void* x, const float* logits, int B, long HW, int C, int nblk, float* part /* [B][nblk][C] */,
-                float* ml /* [B][nblk][2] = {max, sumexp} */, kd_stream_t stream);
+int kd_gca_pool(const void* x, const float* logits /* [n_parts][B*HW]: partial logits, summed per pixel */, int n_parts, int B, long HW,
+                int C, int nblk, float* part /* [B][nblk][C] */, float* ml /* [B][nblk][2] = {max, sumexp} */, kd_stream_t stream);
 int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled /* [B][C] */, kd_stream_t stream);
 /* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); fp16 in/out.  oct_partial (optional, [B][nblk][C/8][2]):
  * fused statistics of `out` in kd_oct_stats form, nblk = kd_elementwise_blocks(HW, C). */

@@ -37,14 +37,14 @@ SIGNATURES = {
     "kd_set_conv_impl": (c_int, [_I]),
     "kd_conv_gemm": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "kd_conv_stats_layout": (c_int, [POINTER(KdConvDesc), POINTER(c_int)]),
-    "kd_conv_gemm_stats": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "kd_conv_gemm_fused": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "kd_linear_small": (c_int, [_P, _I, _I, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
     "kd_sinu_emb": (c_int, [_P, _P, _I, _I, _P, _P]),
     "kd_gn_stats": (c_int, [_P, _I, _L, _I, _I, _I, _I, _P, _I, _P]),
     "kd_gn_finalize": (c_int, [_P, _I, _F, _P, _I, _F, _I, _I, c_double, _F, _P, _P]),
     "kd_gn_apply": (c_int, [_P, _P, _I, _L, _I, _I, _I, _I, _F, _P, _P, _P, _P, _L, _I, _I, _P]),
     "kd_rowdot": (c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
-    "kd_gca_pool": (c_int, [_P, _P, _I, _L, _I, _I, _P, _P, _P]),
+    "kd_gca_pool": (c_int, [_P, _P, _I, _I, _L, _I, _I, _P, _P, _P]),
     "kd_gca_finalize": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "kd_gate_residual": (c_int, [_P, _P, _P, _P, _P, _I, _L, _I, _P]),
     "kd_elementwise_blocks": (c_int, [_L, _I]),

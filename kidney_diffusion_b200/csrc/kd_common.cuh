@@ -63,15 +63,20 @@ __device__ __forceinline__ void h16x8_to_float(const h16x8& in, float* out) {
     out[2 * i + 1] = f.y;
   }
 }
+// {lo = a, hi = b} rounded to nearest-even and saturated to +-65504 in ONE instruction (F2FP.SATFINITE.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t pack_h16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ h16x8 float_to_h16x8(const float* in) {
   h16x8 o;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o.v[i] = __floats2half2_rn(sat16(in[2 * i]), sat16(in[2 * i + 1]));
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t r = pack_h16x2(in[2 * i], in[2 * i + 1]);
+    o.v[i] = *reinterpret_cast<const h162*>(&r);
+  }
   return o;
-}
-__device__ __forceinline__ uint32_t pack_h16x2(float a, float b) {
-  h162 v = __floats2half2_rn(sat16(a), sat16(b));
-  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 // fast intrinsics (ex2.approx / rcp.approx, <= 2 ulp): the library is built without --use_fast_math so that the sampler

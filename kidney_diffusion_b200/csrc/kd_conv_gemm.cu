@@ -35,6 +35,8 @@ struct ConvParams {
   const float* addend_scale;
   void* out;
   float* stats;  // optional per-(row group, channel octet) {sum, sumsq} of the stored output (fused GroupNorm statistics)
+  const float* logit_w;  // optional GlobalContext to_k weight [Cout]: the epilogue also emits per-pixel partial dot products
+  float* logit_parts;    // [Cout / 64][B*H*W] fp32, one partial per 64-column group (summed in fixed order by kd_gca_pool)
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -368,25 +370,59 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
   }
 }
 
-// ---- epilogue role of the CTA-pair kernels (warps 4..11): drains the double-buffered TMEM accumulator tile by tile
-template <int BN>
-__device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CUtensorMap* map_out_ptr, const uint32_t tmem_base,
-                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const uint32_t epi_smem,
-                                                   float* epi_aux, const int warp, const int lane, const uint32_t rank,
-                                                   const int cluster_id, const int num_clusters, const int num_pair_tiles) {
+// ---- epilogue role of the CTA-pair kernels (warps 4..11): drains the double-buffered TMEM accumulator tile by tile.
+// Two sets of 4 warps (one warp of each set per SM sub-partition): set 0 takes the even 64-column groups of a tile, set 1 the
+// odd ones; an "item" is one such group: 128 rows x 64 columns, staged in a 16 KB 128B-swizzled smem tile and written with
+// one TMA store.
+// TADD: the h16 addend tile of every item is fetched by TMA straight into the (double-buffered) staging tile one item ahead
+// and updated in place, instead of 8 row-strided LDG.128 per thread (32 distinct 128-byte lines per warp instruction: the
+// LSU queue, not HBM, bounded the convolutions with a residual -- profiles/r01c ncu of the 1x1 res conv).
+// Bias, gate rows and GlobalContext to_k weights of the whole tile width live in smem and are reloaded only when the
+// tile's (n_tile, batch group) changes, which is rare in the persistent tile order.
+// aux smem: bias[BN] + aux[2][BN] floats
+
+template <int BN, bool TADD>
+__device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CUtensorMap* map_out_ptr, const CUtensorMap* map_add_ptr,
+                                                   uint64_t* add_bar, const uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                                   uint64_t* tmem_empty_bar, const uint32_t epi_smem, float* epi_aux, const int warp,
+                                                   const int lane, const uint32_t rank, const int cluster_id, const int num_clusters,
+                                                   const int num_pair_tiles) {
   const CUtensorMap& map_out = *map_out_ptr;
-  // ================================================================ epilogue (both CTAs): own 128 rows x BN columns
-  // two sets of 4 warps (one warp of each set per SM sub-partition): set 0 takes the even 64-column groups, set 1 the odd
   const int quarter = warp & 3;
   const int set = (warp - 4) >> 2;
-  const bool issuer = (quarter == 0) && (lane == 0);  // this set's TMA-store thread
-  const uint32_t stage = epi_smem + set * EPI_STAGE_BYTES;
-  float* bias_s = epi_aux + set * (3 * EPI_COLS);
-  float* gate_s = bias_s + EPI_COLS;
+  const bool issuer = (quarter == 0) && (lane == 0);  // this set's TMA thread
+  const uint32_t stage0 = epi_smem + set * (TADD ? 2 : 1) * EPI_STAGE_BYTES;
+  float* bias_all = epi_aux;        // [BN]
+  float* aux_all = epi_aux + BN;    // [2][BN]: gate rows of the <= 2 batch images of a tile, or [0] = to_k weights
   const int r = quarter * 32 + lane;
+  const int et = (warp - 4) * 32 + lane;  // 0..255 over both sets
   const int tw = r % p.TW;
   const int th = (r / p.TW) % p.TH;
   const int tb = r / (p.TW * p.TH);
+  const bool gate_smem = (p.addend_scale != nullptr) && (p.TB <= 2);
+  const int Cq = p.Cout >> 2;
+
+  auto set_has_group = [&](int t2) { return (t2 % p.n_tiles) * BN + set * EPI_COLS < p.Cout; };
+  auto load_addend_tile = [&](int t2, int g2, uint32_t buf) {  // issuer thread only
+    int m2 = (t2 / p.n_tiles) * 2 + (int)rank;
+    const int tile_w2 = m2 % p.tiles_w;
+    m2 /= p.tiles_w;
+    const int tile_h2 = m2 % p.tiles_h;
+    const int tile_b2 = m2 / p.tiles_h;
+    const uint32_t bar = smem_u32(&add_bar[set * 2 + buf]);
+    mbar_expect_tx(bar, EPI_STAGE_BYTES);
+    tma_load_5d(stage0 + buf * EPI_STAGE_BYTES, map_add_ptr, bar, (t2 % p.n_tiles) * BN + g2 * EPI_COLS, tile_w2 * p.TW, tile_h2 * p.TH,
+                tile_b2 * p.TB, 0);
+  };
+  // (tn, gn): the next item of this set in visiting order (TADD: the one whose addend tile is requested ahead)
+  int tn = cluster_id, gn = set;
+  uint32_t item = 0;
+  if (TADD && !p.out_f32) {
+    while (tn < num_pair_tiles && !set_has_group(tn)) tn += num_clusters;
+    if (issuer && tn < num_pair_tiles) load_addend_tile(tn, gn, 0);
+  }
+
+  int aux_key = -1;
   uint32_t tile_iter = 0;
   for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
     const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
@@ -399,6 +435,26 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
     const int b = tile_b * p.TB + tb, h = tile_h * p.TH + th, w = tile_w * p.TW + tw;
     const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
     const int n0 = n_tile * BN;
+
+    if (!p.out_f32) {
+      const int key = gate_smem ? tile_b * p.n_tiles + n_tile : n_tile;
+      if (key != aux_key) {  // uniform over all 8 epilogue warps (both sets walk the same tiles)
+        aux_key = key;
+        asm volatile("bar.sync 3, 256;" ::: "memory");  // nobody still reads the old values
+        for (int c = et; c < BN; c += 256) {
+          const bool in = n0 + c < p.Cout;
+          bias_all[c] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + c) : 0.f;
+          if (gate_smem) {
+            const int bb = tile_b * p.TB;
+            aux_all[c] = (in && bb < p.B) ? __ldg(p.addend_scale + (long long)bb * p.Cout + n0 + c) : 0.f;
+            aux_all[BN + c] = (in && bb + 1 < p.B) ? __ldg(p.addend_scale + (long long)(bb + 1) * p.Cout + n0 + c) : 0.f;
+          } else if (p.logit_w != nullptr) {
+            aux_all[c] = in ? __ldg(p.logit_w + n0 + c) : 0.f;
+          }
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
+    }
 
     mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
     tc_fence_after();
@@ -413,58 +469,48 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
         if (row_ok && nc < p.Cout) epilogue_store_chunk(p, acc, nc, b, h, w);
       }
     } else {
-      // h16 output: 64-column groups staged in 128B-swizzled smem and written with one coalesced TMA store each
       const bool tile_in_range = tile_b < p.tiles_b;
-      const int Cq = p.Cout >> 2;
 #pragma unroll 1
       for (int g = set; g < BN / EPI_COLS; g += 2) {
         const int nc0 = n0 + g * EPI_COLS;
         if (nc0 >= p.Cout) break;  // uniform across the set
-        // prefetch this row's 64 addend values (8 x 16 B) before any waiting: their latency hides behind the barrier
-        // and the TMEM load
-        int4 addv[8];
-        const bool has_add = (p.addend != nullptr) && row_ok && !p.addend_f32;
-        if (has_add) {
-          long long off;
-          if (p.out_mode == 1) {
-            const int q4 = nc0 / Cq, c = nc0 - q4 * Cq;
-            off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
-          } else {
-            off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc0;
+        const uint32_t buf = TADD ? (item & 1u) : 0u;
+        const uint32_t stage = stage0 + buf * EPI_STAGE_BYTES;
+        if (!TADD) {
+          // the TMA store that last read this set's staging buffer must have finished reading it
+          if (issuer) tma_store_wait_read<0>();
+          epi_barrier(set);
+        } else {
+          // advance (tn, gn) to the item after this one and request its addend tile into the other buffer
+          gn += 2;
+          if (!(gn < BN / EPI_COLS && n0 + gn * EPI_COLS < p.Cout)) {
+            gn = set;
+            for (tn += num_clusters; tn < num_pair_tiles && !set_has_group(tn); tn += num_clusters) {
+            }
           }
-          const int4* ap = reinterpret_cast<const int4*>(reinterpret_cast<const h16*>(p.addend) + off);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) addv[q] = (nc0 + q * 8 + 8 <= p.Cout) ? ld_stream(ap + q) : make_int4(0, 0, 0, 0);
-        }
-        // bias (and the GlobalContext gate rows of the <= 2 batch images a tile can touch) for these 64 columns go through
-        // smem: per-element global / L1 loads inside the math loop stalled the 8 epilogue warps (ncu: long scoreboard)
-        const bool gate_smem = (p.addend_scale != nullptr) && (p.TB <= 2);
-        if (r < EPI_COLS) {
-          bias_s[r] = (p.bias != nullptr && nc0 + r < p.Cout) ? __ldg(p.bias + nc0 + r) : 0.f;
-        } else if (gate_smem) {
-          const int c = r - EPI_COLS;
-#pragma unroll
-          for (int t2 = 0; t2 < 2; ++t2) {
-            const int bb = tile_b * p.TB + t2;
-            gate_s[t2 * EPI_COLS + c] = (bb < p.B && nc0 + c < p.Cout) ? p.addend_scale[(long long)bb * p.Cout + nc0 + c] : 0.f;
+          epi_barrier(set);  // every thread of the set is done with the previous item (its statistics read the other buffer)
+          if (issuer && tn < num_pair_tiles) {
+            tma_store_wait_read<0>();  // ... and so is the bulk store that drained it
+            load_addend_tile(tn, gn, buf ^ 1u);
           }
+          mbar_wait(smem_u32(&add_bar[set * 2 + buf]), (item >> 1) & 1u);  // this item's addend tile has landed
         }
-        // the TMA store that last read this set's staging buffer must have finished reading it
-        if (issuer) tma_store_wait_read<0>();
-        epi_barrier(set);
-        uint32_t acc2[2][32];
-        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS), acc2[0]);
-        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + 32), acc2[1]);
-        tmem_ld_wait();
+        ++item;
+        const float* bias_s = bias_all + g * EPI_COLS;
+        float lacc = 0.f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const uint32_t* acc = acc2[half];
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * EPI_COLS + half * 32), acc);
+          tmem_ld_wait();
           const int nc = nc0 + half * 32;
           const float* gate = nullptr;
           if (p.addend_scale != nullptr)
-            gate = gate_smem ? (gate_s + tb * EPI_COLS + half * 32) : (p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc);
+            gate = gate_smem ? (aux_all + tb * BN + g * EPI_COLS + half * 32)
+                             : (p.addend_scale + (long long)(row_ok ? b : 0) * p.Cout + nc);
+          const float* lw = aux_all + g * EPI_COLS + half * 32;
           long long add_off = 0;
-          if (p.addend != nullptr && row_ok && p.addend_f32) {
+          if (!TADD && p.addend != nullptr && row_ok) {
             if (p.out_mode == 1) {
               const int q4 = nc / Cq, c = nc - q4 * Cq;
               add_off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
@@ -480,14 +526,21 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
             v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[q * 8 + j]) + v[j], p.act);
+            const uint32_t chunk16 = (uint32_t)(half * 4 + q);
+            const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
             if (p.addend != nullptr && row_ok && nc + q * 8 + 8 <= p.Cout) {
               float a[8];
-              if (p.addend_f32) {
+              if (TADD) {
+                int4 raw;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(dst));
+                h16x8_to_float(*reinterpret_cast<const h16x8*>(&raw), a);
+              } else if (p.addend_f32) {
                 const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + add_off + q * 8);
                 float4 a0 = ap[0], a1 = ap[1];
                 a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-              } else {
-                h16x8_to_float(*reinterpret_cast<const h16x8*>(&addv[half * 4 + q]), a);
+              } else {  // h16 addend of a pixel-shuffle output (not on the UNet's path): plain row loads
+                const int4 raw = ld_stream(reinterpret_cast<const h16*>(p.addend) + add_off + q * 8);
+                h16x8_to_float(*reinterpret_cast<const h16x8*>(&raw), a);
               }
               if (gate != nullptr) {
                 const float4 g0 = *reinterpret_cast<const float4*>(gate + q * 8);
@@ -501,13 +554,20 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = 0.f;
             }
-            const uint32_t chunk16 = (uint32_t)(half * 4 + q);
-            const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
             const h16x8 o8 = float_to_h16x8(v);
             const int4 ov = *reinterpret_cast<const int4*>(&o8);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z), "r"(ov.w) : "memory");
+            if (p.logit_w != nullptr) {  // dot product with the ROUNDED values, as a pass over the stored tensor would see them
+              float f[8];
+              h16x8_to_float(o8, f);
+              const float4 l0 = *reinterpret_cast<const float4*>(lw + q * 8);
+              const float4 l1 = *reinterpret_cast<const float4*>(lw + q * 8 + 4);
+              lacc += f[0] * l0.x + f[1] * l0.y + f[2] * l0.z + f[3] * l0.w + f[4] * l1.x + f[5] * l1.y + f[6] * l1.z + f[7] * l1.w;
+            }
           }
         }
+        if (p.logit_w != nullptr && row_ok)
+          p.logit_parts[(long long)(nc0 / EPI_COLS) * ((long long)p.B * p.H * p.W) + ((long long)b * p.H + h) * p.W + w] = lacc;
         fence_proxy_async_smem();
         epi_barrier(set);
         if (issuer) {
@@ -560,11 +620,12 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
   if (issuer) tma_store_wait_read<0>();  // staging smem must outlive the last bulk stores
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TADD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const ConvParams p,
-                      const int num_pair_tiles) {
+                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                      const __grid_constant__ CUtensorMap map_add, const ConvParams p, const int num_pair_tiles) {
+  constexpr int EPI_BUFS = TADD ? 4 : 2;  // 16 KB staging tiles: one per epilogue set, two with the TMA-fed addend
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
@@ -574,9 +635,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t epi_smem = smem_base + STAGES * STAGE_BYTES;  // 2 x 16 KB swizzled output staging (1024-aligned)
-  uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES;
-  float* epi_aux = reinterpret_cast<float*>(ctrl + 256);  // per epilogue set: bias[64] + gate[2][64]
+  const uint32_t epi_smem = smem_base + STAGES * STAGE_BYTES;  // swizzled output staging tiles (1024-aligned)
+  uint8_t* ctrl = smem_gen + STAGES * STAGE_BYTES + EPI_BUFS * EPI_STAGE_BYTES;
+  uint64_t* add_bar = reinterpret_cast<uint64_t*>(ctrl + 320);  // [set][buffer]: addend tile landed (TADD)
+  float* epi_aux = reinterpret_cast<float*>(ctrl + 384);        // per epilogue set: bias[64] + gate[2][64]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -594,6 +656,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_out);
+    if (TADD) tma_prefetch_desc(&map_add);
     if (p.Cb > 0) tma_prefetch_desc(&map_b);
   }
   if (warp == 1 && lane == 0) {
@@ -607,6 +670,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), 16);  // 8 epilogue warps x 2 CTAs
     }
+    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&add_bar[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), TMEM_COLS);
@@ -683,7 +747,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    pair_epilogue_role<BN>(p, &map_out, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
+    pair_epilogue_role<BN, TADD>(p, &map_out, &map_add, add_bar, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
                            num_clusters, num_pair_tiles);
   }
 
@@ -711,11 +775,11 @@ constexpr int HALO_BYTES = HALO_H * HALO_W * 128;                 // 23 040 B ac
 constexpr int HALO_STAGE_BYTES = ((HALO_BYTES + 1023) / 1024) * 1024;  // stage stride keeps 1024-byte alignment
 constexpr int HALO_AS = 3;
 
-template <int BN, int BS>
+template <int BN, int BS, bool TADD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const ConvParams p,
-                      const int num_pair_tiles) {
+                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                      const __grid_constant__ CUtensorMap map_add, const ConvParams p, const int num_pair_tiles) {
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -725,9 +789,11 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + HALO_AS * HALO_STAGE_BYTES;
+  constexpr int EPI_BUFS = TADD ? 4 : 2;
   const uint32_t epi_smem = b_base + BS * B_HALF_BYTES;
-  uint8_t* ctrl = smem_gen + HALO_AS * HALO_STAGE_BYTES + BS * B_HALF_BYTES + 2 * EPI_STAGE_BYTES;
-  float* epi_aux = reinterpret_cast<float*>(ctrl + 256);
+  uint8_t* ctrl = smem_gen + HALO_AS * HALO_STAGE_BYTES + BS * B_HALF_BYTES + EPI_BUFS * EPI_STAGE_BYTES;
+  uint64_t* add_bar = reinterpret_cast<uint64_t*>(ctrl + 320);
+  float* epi_aux = reinterpret_cast<float*>(ctrl + 384);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* a_empty = a_full + HALO_AS;
   uint64_t* b_full = a_empty + HALO_AS;
@@ -749,6 +815,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_out);
+    if (TADD) tma_prefetch_desc(&map_add);
     if (p.Cb > 0) tma_prefetch_desc(&map_b);
   }
   if (warp == 1 && lane == 0) {
@@ -767,6 +834,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), 16);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&add_bar[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), TMEM_COLS);
@@ -847,7 +915,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    pair_epilogue_role<BN>(p, &map_out, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
+    pair_epilogue_role<BN, TADD>(p, &map_out, &map_add, add_bar, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
                            num_clusters, num_pair_tiles);
   }
 
@@ -964,14 +1032,52 @@ int make_out_map(CUtensorMap* m, const ConvParams& p, void* out) {
   return encode_map(m, out, 5, dims, str, box);
 }
 
-template <int BN, int STAGES>
+// TADD (h16 addend, plain NHWC output): the addend tile is TMA-fed into double-buffered staging, paid for with ring stages
+template <int BN, int STAGES, bool TADD>
 int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 2 * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                       2 * 3 * EPI_COLS * 4 /*bias + gate staging*/;
+  constexpr int SMEM = STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + (TADD ? 4 : 2) * EPI_STAGE_BYTES + 1024 /*align slack*/ +
+                       384 /*barriers*/ + 3 * BN * 4 /*bias + gate / to_k staging*/;
   static_assert(SMEM <= 232448, "pair kernel exceeds the 227 KB shared-memory limit");
-  CUtensorMap mo = ma;
+  CUtensorMap mo = ma, madd = ma;
   if (!p.out_f32) {
     int rc = make_out_map(&mo, p, p.out);
+    if (rc) return rc;
+    madd = mo;
+    if (TADD) {
+      rc = make_out_map(&madd, p, const_cast<void*>(p.addend));
+      if (rc) return rc;
+    }
+  }
+  static bool configured = false;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured) {
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, STAGES, TADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured = true;
+    }
+  }
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  const long long pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+  KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
+  int clusters = kd_num_sms() / 2;
+  if (pair_tiles < clusters) clusters = (int)pair_tiles;
+  conv_gemm_pair_kernel<BN, STAGES, TADD><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+template <int BN, int BS, bool TADD>
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
+  constexpr int SMEM = HALO_AS * HALO_STAGE_BYTES + BS * (BN / 2) * BK * 2 + (TADD ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 384 +
+                       3 * BN * 4;
+  static_assert(SMEM <= 232448, "halo kernel exceeds the 227 KB shared-memory limit");
+  CUtensorMap mo, madd;
+  int rc = make_out_map(&mo, p, p.out);
+  if (rc) return rc;
+  madd = mo;
+  if (TADD) {
+    rc = make_out_map(&madd, p, const_cast<void*>(p.addend));
     if (rc) return rc;
   }
   static bool configured = false;
@@ -979,7 +1085,7 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   {
     std::lock_guard<std::mutex> lock(mu);
     if (!configured) {
-      KD_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, BS, TADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured = true;
     }
   }
@@ -988,33 +1094,7 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
   int clusters = kd_num_sms() / 2;
   if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_pair_kernel<BN, STAGES><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, p, (int)pair_tiles);
-  KD_LAUNCH_CHECK();
-  return KD_OK;
-}
-
-template <int BN, int BS>
-int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
-  constexpr int SMEM = HALO_AS * HALO_STAGE_BYTES + BS * (BN / 2) * BK * 2 + 2 * EPI_STAGE_BYTES + 1024 + 256 + 2 * 3 * EPI_COLS * 4;
-  static_assert(SMEM <= 232448, "halo kernel exceeds the 227 KB shared-memory limit");
-  CUtensorMap mo;
-  int rc = make_out_map(&mo, p, p.out);
-  if (rc) return rc;
-  static bool configured = false;
-  static std::mutex mu;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (!configured) {
-      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-      configured = true;
-    }
-  }
-  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
-  const long long pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
-  KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
-  int clusters = kd_num_sms() / 2;
-  if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_halo_kernel<BN, BS><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, p, (int)pair_tiles);
+  conv_gemm_halo_kernel<BN, BS, TADD><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -1076,11 +1156,12 @@ extern "C" int kd_conv_stats_layout(const KdConvDesc* d, int* layout) {
 
 extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
                             const void* addend, const float* addend_scale, void* out, kd_stream_t stream_) {
-  return kd_conv_gemm_stats(d, xa, xb, w, bias, addend, addend_scale, out, nullptr, stream_);
+  return kd_conv_gemm_fused(d, xa, xb, w, bias, addend, addend_scale, out, nullptr, nullptr, nullptr, stream_);
 }
 
-extern "C" int kd_conv_gemm_stats(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
-                                  const void* addend, const float* addend_scale, void* out, float* stats, kd_stream_t stream_) {
+extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
+                                  const void* addend, const float* addend_scale, void* out, float* stats, const float* logit_w,
+                                  float* logit_parts, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(d && xa && w && out, "kd_conv_gemm: null argument");
   KD_REQUIRE(d->mode >= 0 && d->mode <= 2, "kd_conv_gemm: bad mode %d", d->mode);
@@ -1112,7 +1193,7 @@ extern "C" int kd_conv_gemm_stats(const KdConvDesc* d, const void* xa, const voi
   p.chunks_a = d->Ca / BK;
   p.chunks_per_tap = (d->Ca + d->Cb) / BK;
   p.num_kb = taps * p.chunks_per_tap;
-  p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out; p.stats = stats;
+  p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out; p.stats = stats; p.logit_w = logit_w; p.logit_parts = logit_parts;
 
   // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel;
   // 3x3 convolutions on images of at least 16 x 8 pixels use the halo-reuse variant (impl 4 forces the tap-loop pair kernel)
@@ -1153,18 +1234,29 @@ extern "C" int kd_conv_gemm_stats(const KdConvDesc* d, const void* xa, const voi
     rc = encode_map(&mw, w, 2, dims, str, box);
     if (rc) return rc;
   }
-  if (stats != nullptr) {
+  if (stats != nullptr || logit_w != nullptr) {
     int lay[3];
     kd_conv_stats_layout(d, lay);
-    KD_REQUIRE(lay[0] > 0, "kd_conv_gemm_stats: this shape / kernel does not produce fused statistics (see kd_conv_stats_layout)");
+    KD_REQUIRE(lay[0] > 0, "kd_conv_gemm_fused: this shape / kernel does not produce fused statistics (see kd_conv_stats_layout)");
+    KD_REQUIRE(logit_w == nullptr || (logit_parts != nullptr && addend_scale == nullptr && d->Cout % 64 == 0),
+               "kd_conv_gemm_fused: fused GlobalContext logits need Cout %% 64 == 0, an output buffer and no gate");
   }
+  const bool tadd = use_pair && addend != nullptr && !d->addend_f32 && !d->out_f32 && d->out_mode == 0;
   if (use_halo) {
-    if (BN == 256) return launch_halo<256, 7>(ma, mb, mw, p, stream);
-    return launch_halo<128, 10>(ma, mb, mw, p, stream);
+    if (tadd) {
+      if (BN == 256) return launch_halo<256, 5, true>(ma, mb, mw, p, stream);
+      return launch_halo<128, 8, true>(ma, mb, mw, p, stream);
+    }
+    if (BN == 256) return launch_halo<256, 7, false>(ma, mb, mw, p, stream);
+    return launch_halo<128, 10, false>(ma, mb, mw, p, stream);
   }
   if (use_pair) {
-    if (BN == 256) return launch_pair<256, 6>(ma, mb, mw, p, stream);
-    return launch_pair<128, 8>(ma, mb, mw, p, stream);
+    if (tadd) {
+      if (BN == 256) return launch_pair<256, 4, true>(ma, mb, mw, p, stream);
+      return launch_pair<128, 6, true>(ma, mb, mw, p, stream);
+    }
+    if (BN == 256) return launch_pair<256, 5, false>(ma, mb, mw, p, stream);
+    return launch_pair<128, 8, false>(ma, mb, mw, p, stream);
   }
   if (BN == 128) return launch<128, 3>(ma, mb, mw, p, grid, stream);
   return launch<64, 4>(ma, mb, mw, p, grid, stream);

@@ -1,8 +1,8 @@
 // The two "edge" convolutions of the UNet whose shapes are not tensor-core friendly on their own:
 //   * CrossEmbedLayer input convs (Cin = 3..10 image channels, kernels 3/7/15): an im2col panel builder (NCHW fp32 ->
 //     [pixels, Kp] h16) feeding kd_conv_gemm mode 2, where the three kernels are merged into one 15x15 weight matrix.
-//   * final_conv (3x3, Cout = 3) on cat(x, lowres_cond_img): HBM-bound, a shared-memory tiled SIMT kernel that also
-//     converts NHWC h16 -> NCHW fp32.
+//   * final_conv (3x3, Cout = 3) on cat(x, lowres_cond_img): HBM-bound, shared-memory halo tiles + mma.sync with a split
+//     (hi + lo) fp16 filter; also converts NHWC h16 -> NCHW fp32.
 #include "kd_common.cuh"
 
 namespace {
@@ -55,25 +55,49 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------ final conv
+// 3x3, Cout <= 4: HBM-bound (one read of the 128-channel activation).  Per 8 x 32 pixel tile the halo is staged in shared
+// memory 32 channels at a time; each warp owns one tile row (two m16 pixel groups) and runs mma.sync m16n8k16 with the
+// fp32 filter split into fp16 hi + lo parts (two MMAs), so the filter keeps ~22 significant bits as in the fp32 reference.
+// The <= 4 fp32 NCHW extra channels (lowres_cond_img) and the bias are added per pixel in fp32 SIMT, which is also the
+// coalesced NCHW writer.
 constexpr int FC_TH = 8, FC_TW = 32, FC_CH = 32;           // 256 pixels per block, 32-channel chunks
 constexpr int FC_HH = FC_TH + 2, FC_HW = FC_TW + 2;         // halo tile
-constexpr int FC_PIX_STRIDE = FC_CH + 8;                    // h16 elements per halo pixel (80 B: conflict-free 16 B reads)
+constexpr int FC_PIX_STRIDE = FC_CH + 8;                    // h16 elements per halo pixel (80 B: conflict-free ldmatrix rows)
 constexpr int FC_MAXCO = 4;
+constexpr int FC_WK = FC_CH + 8;                            // padded k stride of the staged filter rows
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ out, int H, int W, int Cout) {
   __shared__ __align__(16) h16 s_act[FC_HH * FC_HW * FC_PIX_STRIDE];
-  __shared__ __align__(16) float s_w[FC_MAXCO * 9 * FC_CH];
+  __shared__ __align__(16) h16 s_w[2][9][8][FC_WK];  // [hi / lo][tap][n][k]
   __shared__ float s_xb[4 * FC_HH * FC_HW];
+  __shared__ float s_wb[FC_MAXCO * 9 * 4];
+  __shared__ float s_res[FC_MAXCO][FC_TH][FC_TW];
   const int Ctot = Ca + Cb;
   const int b = blockIdx.z, h0 = blockIdx.y * FC_TH, w0 = blockIdx.x * FC_TW;
-  const int ty = threadIdx.x / FC_TW, tx = threadIdx.x % FC_TW;
-  float acc[FC_MAXCO] = {0.f, 0.f, 0.f, 0.f};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+
+  // rows of the filter tile that no output channel uses stay zero
+  for (int i = threadIdx.x; i < 2 * 9 * 8 * FC_WK; i += 256) (&s_w[0][0][0][0])[i] = __float2half(0.f);
+
+  // ldmatrix lane addressing of an m16 x k16 A fragment: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_kof = (lane >> 4) * 8;
+  const uint32_t s_act_u32 = (uint32_t)__cvta_generic_to_shared(s_act);
 
   for (int c0 = 0; c0 < Ca; c0 += FC_CH) {
     __syncthreads();
-    // halo activations: FC_HH*FC_HW pixels x 4 vectors of 8 channels
     for (int i = threadIdx.x; i < FC_HH * FC_HW * 4; i += 256) {
       const int v = i & 3, pix = i >> 2;
       const int py = pix / FC_HW, px = pix % FC_HW;
@@ -84,30 +108,46 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__
     }
     for (int i = threadIdx.x; i < Cout * 9 * FC_CH; i += 256) {
       const int c = i % FC_CH, tap = (i / FC_CH) % 9, co = i / (FC_CH * 9);
-      s_w[i] = w[((long)co * 9 + tap) * Ctot + c0 + c];
+      const float wf = w[((long)co * 9 + tap) * Ctot + c0 + c];
+      const h16 hi = __float2half_rn(wf);
+      s_w[0][tap][co][c] = hi;
+      s_w[1][tap][co][c] = __float2half_rn(wf - __half2float(hi));
     }
     __syncthreads();
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const int py = ty + tap / 3, px = tx + tap % 3;
-      const h16* ap = &s_act[(py * FC_HW + px) * FC_PIX_STRIDE];
+      const int py = warp + tap / 3, dx = tap % 3;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        float a[8];
-        h16x8_to_float(*reinterpret_cast<const h16x8*>(ap + v * 8), a);
+      for (int ks = 0; ks < FC_CH / 16; ++ks) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&s_w[0][tap][lane >> 2][ks * 16 + (lane & 3) * 2]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&s_w[0][tap][lane >> 2][ks * 16 + 8 + (lane & 3) * 2]);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&s_w[1][tap][lane >> 2][ks * 16 + (lane & 3) * 2]);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&s_w[1][tap][lane >> 2][ks * 16 + 8 + (lane & 3) * 2]);
 #pragma unroll
-        for (int co = 0; co < FC_MAXCO; ++co) {
-          if (co < Cout) {
-            const float4 wa = *reinterpret_cast<const float4*>(&s_w[(co * 9 + tap) * FC_CH + v * 8]);
-            const float4 wb = *reinterpret_cast<const float4*>(&s_w[(co * 9 + tap) * FC_CH + v * 8 + 4]);
-            acc[co] += a[0] * wa.x + a[1] * wa.y + a[2] * wa.z + a[3] * wa.w + a[4] * wb.x + a[5] * wb.y + a[6] * wb.z + a[7] * wb.w;
-          }
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t a0, a1, a2, a3;
+          const int px = mt * 16 + a_row + dx;
+          ldmatrix_x4(s_act_u32 + ((py * FC_HW + px) * FC_PIX_STRIDE + ks * 16 + a_kof) * 2, a0, a1, a2, a3);
+          mma_16816(acc[mt], a0, a1, a2, a3, bh0, bh1);
+          mma_16816(acc[mt], a0, a1, a2, a3, bl0, bl1);
         }
       }
     }
   }
+  // accumulator fragment: rows lane/4 and lane/4 + 8 of the m-tile, columns (lane%4)*2 + {0, 1}
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int n0 = (lane & 3) * 2, r = lane >> 2;
+    if (n0 < FC_MAXCO) {
+      s_res[n0][warp][mt * 16 + r] = acc[mt][0];
+      s_res[n0 + 1][warp][mt * 16 + r] = acc[mt][1];
+      s_res[n0][warp][mt * 16 + r + 8] = acc[mt][2];
+      s_res[n0 + 1][warp][mt * 16 + r + 8] = acc[mt][3];
+    }
+  }
+  const int ty = threadIdx.x / FC_TW, tx = threadIdx.x % FC_TW;
+  float extra[FC_MAXCO] = {0.f, 0.f, 0.f, 0.f};
   if (Cb > 0) {
-    __syncthreads();
     for (int i = threadIdx.x; i < Cb * FC_HH * FC_HW; i += 256) {
       const int pix = i % (FC_HH * FC_HW), c = i / (FC_HH * FC_HW);
       const int py = pix / FC_HW, px = pix % FC_HW;
@@ -116,16 +156,18 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__
     }
     for (int i = threadIdx.x; i < Cout * 9 * Cb; i += 256) {
       const int c = i % Cb, tap = (i / Cb) % 9, co = i / (Cb * 9);
-      s_w[i] = w[((long)co * 9 + tap) * Ctot + Ca + c];
+      s_wb[i] = w[((long)co * 9 + tap) * Ctot + Ca + c];
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  if (Cb > 0) {
     for (int tap = 0; tap < 9; ++tap) {
       const int py = ty + tap / 3, px = tx + tap % 3;
       for (int c = 0; c < Cb; ++c) {
         const float a = s_xb[c * FC_HH * FC_HW + py * FC_HW + px];
 #pragma unroll
         for (int co = 0; co < FC_MAXCO; ++co)
-          if (co < Cout) acc[co] += a * s_w[(co * 9 + tap) * Cb + c];
+          if (co < Cout) extra[co] += a * s_wb[(co * 9 + tap) * Cb + c];
       }
     }
   }
@@ -133,7 +175,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__
   if (gy < H && gx < W) {
 #pragma unroll
     for (int co = 0; co < FC_MAXCO; ++co)
-      if (co < Cout) out[(((long)b * Cout + co) * H + gy) * W + gx] = acc[co] + (bias ? bias[co] : 0.f);
+      if (co < Cout) out[(((long)b * Cout + co) * H + gy) * W + gx] = s_res[co][ty][tx] + extra[co] + (bias ? bias[co] : 0.f);
   }
 }
 

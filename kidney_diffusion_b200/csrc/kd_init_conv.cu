@@ -13,8 +13,9 @@
 // stays resident, every pass computes two output rows (two TMEM accumulators share each TMA-streamed weight chunk), and
 // each new output row costs one new halo row of SIMT fill (7 KB) instead of a 180 KB im2col panel row.
 //
-// Warp roles (320 threads, persistent CTA, one per SM): warp 0 = weight TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2-5 = epilogue (TMEM -> bias / addend -> fp16 NHWC), warps 6-9 = halo-row fillers (NCHW fp32 -> shifted fp16).
+// Warp roles (448 threads, persistent CTA, one per SM): warp 0 = weight TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2-9 = epilogue (one set of 4 per output row: TMEM -> bias / addend -> fp16 NHWC), warps 10-13 = halo-row fillers
+// (NCHW fp32 -> shifted fp16).
 #include "kd_tc.cuh"
 
 namespace {
@@ -24,7 +25,7 @@ constexpr int IC_BLOCKS = 17;                   // 128-byte blocks per (halo row
 constexpr int IC_ROWC_BYTES = IC_BLOCKS * 128;  // 2176
 constexpr int IC_HALO_W = IC_BLOCKS * 8 + 7;    // 143 source elements
 constexpr int IC_BSTAGES = 4;
-constexpr int IC_THREADS = 320;
+constexpr int IC_THREADS = 448;
 constexpr int IC_FILL_THREADS = 128;
 
 struct InitParams {
@@ -35,6 +36,7 @@ struct InitParams {
   const float* bias;
   const h16* addend;
   h16* out;
+  int dbg;
 };
 
 template <int BN>
@@ -49,7 +51,8 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
   const uint32_t ring_base = smem_base + IC_BSTAGES * B_STAGE_BYTES;
   uint8_t* ring_gen = smem_gen + IC_BSTAGES * B_STAGE_BYTES;
   const int ring_bytes = p.ring * p.C * IC_ROWC_BYTES;
-  uint8_t* ctrl = ring_gen + ring_bytes;
+  uint8_t* stage_gen = ring_gen + ring_bytes;  // 8 epilogue warps x 4 KB
+  uint8_t* ctrl = stage_gen + 8 * 4096;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* b_empty = b_full + IC_BSTAGES;
   uint64_t* rows_full = b_empty + IC_BSTAGES;  // [2]
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&rows_full[a]), IC_FILL_THREADS);
       mbar_init(smem_u32(&tmem_full[a]), 1);
-      mbar_init(smem_u32(&tmem_empty[a]), 4);
+      mbar_init(smem_u32(&tmem_empty[a]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -105,19 +108,23 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
+    // (one thread issues ~90 MMAs per pass: all operand addresses come from wrap-around counters, no div / mod on this path)
     if (lane == 0) {
       uint32_t cc = 0, q = 0;
+      const uint64_t a_desc0 = make_nosw_desc(ring_base, 128, 128);
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int seg = (u / p.n_strips) % p.n_segs;
         const int r0 = seg * p.rows_seg;
         const int rows = min(p.rows_seg, p.H - r0);
         const int passes = (rows + 1) >> 1;
+        int s0 = 0;  // ring slot of halo row 2 * pl
         for (int pl = 0; pl < passes; ++pl, ++q) {
           const uint32_t a = q & 1, ph = (q >> 1) & 1;
           mbar_wait(smem_u32(&tmem_empty[a]), ph ^ 1u);
           mbar_wait(smem_u32(&rows_full[a]), ph);
           tc_fence_after();
           const uint32_t d0 = tmem_base + a * (2 * BN);
+          int c = 0, slot = s0, pair = 0;
           for (int j = 0; j < p.n_chunks; ++j, ++cc) {
             const int s = cc % IC_BSTAGES;
             mbar_wait(smem_u32(&b_full[s]), (cc / IC_BSTAGES) & 1);
@@ -125,27 +132,35 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
             const uint64_t b_desc = make_sw128_desc(smem_base + s * B_STAGE_BYTES);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const int pair = j * 4 + t;
               if (pair < p.n_pairs) {
-                const int ky = pair / p.C, c = pair - ky * p.C;
-#pragma unroll
-                for (int o = 0; o < 2; ++o) {
-                  const int slot = (2 * pl + o + ky) % p.ring;
-                  const uint64_t a_desc = make_nosw_desc(ring_base + (slot * p.C + c) * IC_ROWC_BYTES, 128, 128);
-                  umma_f16(d0 + o * BN, a_desc, b_desc + (uint64_t)(2 * t), IDESC, pair != 0 ? 1u : 0u);
+                const int slot1 = (slot + 1 == p.ring) ? 0 : slot + 1;
+                if (!(p.dbg & 2)) {
+                  const uint32_t acc = pair != 0 ? 1u : 0u;
+                  umma_f16(d0, a_desc0 + (uint64_t)((slot * p.C + c) * (IC_ROWC_BYTES >> 4)), b_desc + (uint64_t)(2 * t), IDESC, acc);
+                  umma_f16(d0 + BN, a_desc0 + (uint64_t)((slot1 * p.C + c) * (IC_ROWC_BYTES >> 4)), b_desc + (uint64_t)(2 * t), IDESC,
+                           acc);
+                }
+                ++pair;
+                if (++c == p.C) {
+                  c = 0;
+                  slot = slot1;
                 }
               }
             }
             umma_commit(smem_u32(&b_empty[s]));
           }
           umma_commit(smem_u32(&tmem_full[a]));
+          s0 += 2;
+          if (s0 >= p.ring) s0 -= p.ring;
         }
       }
     }
-  } else if (warp < 6) {
-    // ================================================================ epilogue
+  } else if (warp < 10) {
+    // ================================================================ epilogue: warp set o (4 warps) owns output row o of a pass
     const int quarter = warp & 3;
+    const int o = (warp - 2) >> 2;
     const int col = quarter * 32 + lane;
+    uint8_t* stage_w = stage_gen + (warp - 2) * 4096;
     uint32_t q = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int strip = u % p.n_strips;
@@ -157,39 +172,53 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
       const int x = strip * IC_M + col;
       for (int pl = 0; pl < passes; ++pl, ++q) {
         const uint32_t a = q & 1, ph = (q >> 1) & 1;
+        const int y = r0 + 2 * pl + o;
+        const bool ok = (y < r0 + rows) && (x < p.W);
+        const long long off = (((long long)b * p.H + y) * p.W + x) * p.Cout;
+        // the whole addend row of this pixel is requested before waiting for the accumulator (hides the HBM latency)
+        int4 add[BN / 8];
+        if (ok && p.addend != nullptr) {
+#pragma unroll
+          for (int g = 0; g < BN / 8; ++g) add[g] = *reinterpret_cast<const int4*>(p.addend + off + g * 8);  // may alias out
+        }
         mbar_wait(smem_u32(&tmem_full[a]), ph);
         tc_fence_after();
-#pragma unroll 1
-        for (int o = 0; o < 2; ++o) {
-          const int y = r0 + 2 * pl + o;
-          const bool ok = (y < r0 + rows) && (x < p.W);
-          const long long off = (((long long)b * p.H + y) * p.W + x) * p.Cout;
-#pragma unroll 1
-          for (int chunk = 0; chunk < BN / 32; ++chunk) {
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (2 * BN) + o * BN + chunk * 32, acc);
-            int4 add[4];
-            const bool live = ok && chunk * 32 < p.Cout;
-            if (live && p.addend != nullptr) {
+        // 64-channel halves are transposed through a per-warp 4 KB staging tile (16-byte units XOR-swizzled by pixel) so that
+        // every global store instruction writes four whole 128-byte pixel-halves
+        const int x_warp = strip * IC_M + quarter * 32;
+        const bool row_live = (y < r0 + rows);
+        const long long off_warp = (((long long)b * p.H + y) * p.W + x_warp) * p.Cout;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) add[g] = *reinterpret_cast<const int4*>(p.addend + off + chunk * 32 + g * 8);  // may alias out
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (2 * BN) + o * BN + chunk * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]) + bias_smem[chunk * 32 + g * 8 + j];
+            if (ok && p.addend != nullptr) {
+              float av[8];
+              h16x8_to_float(*reinterpret_cast<const h16x8*>(&add[chunk * 4 + g]), av);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += av[j];
             }
-            tmem_ld_wait();
-            if (!live) continue;
+            h16x8 o8 = float_to_h16x8(v);
+            const int unit = (chunk & 1) * 4 + g;
+            *reinterpret_cast<h16x8*>(stage_w + lane * 128 + ((unit ^ (lane & 7)) << 4)) = o8;
+          }
+          if (chunk & 1) {
+            __syncwarp();
+            if (row_live && !(p.dbg & 4)) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]) + bias_smem[chunk * 32 + g * 8 + j];
-              if (p.addend != nullptr) {
-                float av[8];
-                h16x8_to_float(*reinterpret_cast<const h16x8*>(&add[g]), av);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += av[j];
+              for (int i = 0; i < 8; ++i) {
+                const int px = i * 4 + (lane >> 3), unit = lane & 7;
+                const int4 val = *reinterpret_cast<const int4*>(stage_w + px * 128 + ((unit ^ (px & 7)) << 4));
+                if (x_warp + px < p.W) st_stream(p.out + off_warp + (long long)px * p.Cout + (chunk >> 1) * 64 + unit * 8, val);
               }
-              h16x8 o8 = float_to_h16x8(v);
-              *reinterpret_cast<h16x8*>(p.out + off + chunk * 32 + g * 8) = o8;
             }
+            __syncwarp();
           }
         }
         tc_fence_before();
@@ -199,7 +228,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
     }
   } else {
     // ================================================================ halo-row fillers
-    const int f = threadIdx.x - 192;
+    const int f = threadIdx.x - 320;
     const int units_per_row = p.C * IC_BLOCKS * 8;  // 16-byte units of one halo row (all channels)
     uint32_t q = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -231,6 +260,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
           const int e0 = (un >> 3) * 8 + (un & 7);
           const int gy = r0 + rr - pad;
           float v[8];
+          if (p.dbg & 1) continue;
           if (gy >= 0 && gy < p.H) {
             const float* src = img + ((long long)c * p.H + gy) * p.W;
 #pragma unroll
@@ -262,7 +292,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
 
 template <int BN>
 int launch_init(const CUtensorMap& mw, const InitParams& p, cudaStream_t stream) {
-  const size_t smem = 1024 + IC_BSTAGES * BN * 128 + (size_t)p.ring * p.C * IC_ROWC_BYTES + 128 + BN * sizeof(float);
+  const size_t smem = 1024 + IC_BSTAGES * BN * 128 + (size_t)p.ring * p.C * IC_ROWC_BYTES + 8 * 4096 + 128 + BN * sizeof(float);
   KD_REQUIRE(smem <= 227 * 1024, "kd_init_conv: shared memory %zu exceeds the SM limit", smem);
   static size_t configured = 0;
   if (smem > configured) {
@@ -276,6 +306,9 @@ int launch_init(const CUtensorMap& mw, const InitParams& p, cudaStream_t stream)
 }
 
 }  // namespace
+
+static int g_init_dbg = 0;
+extern "C" int kd_exp_init_conv_debug(int m) { g_init_dbg = m; return 0; }
 
 extern "C" int kd_init_conv_kp(int C, int ksize) { return ((ksize * C * 16 + 63) / 64) * 64; }
 
@@ -300,6 +333,7 @@ extern "C" int kd_init_conv(const float* x, int B, int C, int H, int W, int ksiz
   p.n_chunks = kd_ceil_div(p.n_pairs, 4);
   p.ring = ksize + 3;
   p.bias = bias;
+  p.dbg = g_init_dbg;
   p.addend = reinterpret_cast<const h16*>(addend);
   p.out = reinterpret_cast<h16*>(out);
   CUtensorMap mw;

@@ -196,8 +196,15 @@ __global__ void rowdot_kernel(const h16* __restrict__ x, const float* __restrict
 }
 
 // Softmax-weighted channel pooling, one block per (pixel chunk, b): partial[b][blk][c] = sum_n exp(l_n - m_blk) x[n,c]
-__global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restrict__ logits, long HW, int C, int nblk,
-                                float* __restrict__ part, float* __restrict__ ml) {
+// logits may arrive as n_parts partial dot products per pixel ([n_parts][B*HW], from the conv epilogue): summed in fixed order
+__device__ __forceinline__ float gca_logit(const float* __restrict__ lg, long p, int n_parts, long part_stride) {
+  float v = lg[p];
+  for (int k = 1; k < n_parts; ++k) v += lg[p + k * part_stride];
+  return v;
+}
+
+__global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restrict__ logits, int n_parts, long part_stride, long HW,
+                                int C, int nblk, float* __restrict__ part, float* __restrict__ ml) {
   extern __shared__ float sm[];  // max(T, lanes*C) floats
   __shared__ float s_red[32];
   __shared__ float s_m;
@@ -213,7 +220,7 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
   const float* lg = logits + (long)b * HW;
   // block max of the chunk's logits
   float m = -INFINITY;
-  for (long p = p0 + threadIdx.x; p < p1; p += T) m = fmaxf(m, lg[p]);
+  for (long p = p0 + threadIdx.x; p < p1; p += T) m = fmaxf(m, gca_logit(lg, p, n_parts, part_stride));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -228,7 +235,7 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
   float l = 0.f;
   const h16* xb = x + (long)b * HW * C + (long)o * 8;
   for (long p = p0 + pl; p < p1; p += lanes) {
-    const float e = __expf(lg[p] - m);
+    const float e = __expf(gca_logit(lg, p, n_parts, part_stride) - m);
     int4 raw = ld_stream(xb + p * C);
     float v[8];
     h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
@@ -636,14 +643,14 @@ extern "C" int kd_rowdot(const void* x, const float* w, const float* bias, float
   return KD_OK;
 }
 
-extern "C" int kd_gca_pool(const void* x, const float* logits, int B, long HW, int C, int nblk, float* part, float* ml,
+extern "C" int kd_gca_pool(const void* x, const float* logits, int n_parts, int B, long HW, int C, int nblk, float* part, float* ml,
                            kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(x && logits && part && ml && B > 0 && HW > 0 && nblk > 0, "kd_gca_pool: bad argument");
+  KD_REQUIRE(x && logits && part && ml && B > 0 && HW > 0 && nblk > 0 && n_parts >= 1, "kd_gca_pool: bad argument");
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
   const size_t smem = sizeof(float) * (size_t)T * 8;
-  gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const h16*>(x), logits, HW, C, nblk, part, ml);
+  gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const h16*>(x), logits, n_parts, (long)B * HW, HW, C, nblk, part, ml);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -21,7 +21,7 @@ launch_count = 0  # kernels launched through this module (bench.py reports it as
 conv_profile = None  # bench.py sets this to a list: every tensor-core GEMM launch appends (flops, start_event, end_event)
 
 
-op_profile = None  # bench / profiling: list of (op name, start_event, end_event) for EVERY op when set
+op_profile = None  # bench / profiling: list of (op name, start_event, end_event, tensor bytes in + out) for EVERY op when set
 
 
 def _timed(fn):
@@ -36,7 +36,13 @@ def _timed(fn):
         e0.record()
         out = fn(*a, **k)
         e1.record()
-        op_profile.append((fn.__name__, e0, e1))
+        nbytes = 0  # bytes of the distinct tensors the op touches once each: the HBM-traffic floor of the launch
+        seen = set()
+        for t in list(a) + list(k.values()) + (list(out) if isinstance(out, (tuple, list)) else [out]):
+            if isinstance(t, torch.Tensor) and t.data_ptr() not in seen:
+                seen.add(t.data_ptr())
+                nbytes += t.numel() * t.element_size()
+        op_profile.append((fn.__name__, e0, e1, nbytes))
         return out
 
     return wrapper
@@ -158,8 +164,11 @@ def gn_finalize_oct(stats_a, scale_a, stats_b, scale_b, group_size, num_groups, 
 
 @_timed
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
-              addend=None, addend_scale=None, out=None, want_stats=False):
-    """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32)."""
+              addend=None, addend_scale=None, out=None, want_stats=False, logit_w=None):
+    """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32).
+    want_stats / logit_w: ask the epilogue for fused GroupNorm statistics / GlobalContext logits of the output; they are
+    attached to the result as `_kd_stats` / `_kd_logits` when this shape's kernel can emit them (else the consumer runs
+    its standalone kernel)."""
     _chk(xa, ACT_DTYPE, "xa")
     _chk(w, ACT_DTYPE, "w")
     B, Hin, Win, Ca = xa.shape
@@ -186,14 +195,22 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
         assert addend_scale.shape == (B, Cout)
     d = KdConvDesc(mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, 1 if out_f32 else 0, addend_f32)
     stats = None
-    if want_stats:
+    lay = None
+    if (want_stats or logit_w is not None) and FUSED_STATS:
         lay = (ctypes.c_int * 3)()
         check(lib().kd_conv_stats_layout(ctypes.byref(d), lay), "kd_conv_stats_layout")
-        if lay[0] > 0:
+        if lay[0] > 0 and want_stats:
             stats = OctStats(torch.empty((lay[0], Cout // 8, 2), device=xa.device, dtype=torch.float32), 4, lay[1], lay[2], B, Cout // 8)
+    logit_parts = None
+    if logit_w is not None and lay is not None and lay[0] > 0 and out_mode == 0 and Cout % 64 == 0 and addend_scale is None:
+        _chk(logit_w, torch.float32, "logit_w")
+        logit_parts = torch.empty((Cout // 64, B, H * W), device=xa.device, dtype=torch.float32)
     with _ConvTimer(2.0 * B * H * W * Cout * taps * (Ca + Cb), (mode, B, H, W, Ca + Cb, Cout, ksize if mode == 0 else 2)):
-        check(lib().kd_conv_gemm_stats(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
-                                       _ptr(out), None if stats is None else _ptr(stats.partial), _stream()), "kd_conv_gemm")
+        check(lib().kd_conv_gemm_fused(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
+                                       _ptr(out), None if stats is None else _ptr(stats.partial),
+                                       None if logit_parts is None else _ptr(logit_w), _ptr(logit_parts), _stream()), "kd_conv_gemm")
+    if logit_parts is not None:
+        out._kd_logits = logit_parts
     _count()
     if stats is not None:
         out._kd_stats = stats
@@ -325,12 +342,14 @@ def rowdot(x, w, bias):
 
 @_timed
 def gca_pool(x, logits):
+    """logits: [B, HW] or [n_parts, B, HW] partial logits (summed per pixel in fixed order inside the kernel)."""
     B, H, W, C = x.shape
     HW = H * W
+    n_parts = logits.shape[0] if logits.dim() == 3 else 1
     nblk = _nblk(HW, C, B)
     part = torch.empty((B, nblk, C), device=x.device, dtype=torch.float32)
     ml = torch.empty((B, nblk, 2), device=x.device, dtype=torch.float32)
-    check(lib().kd_gca_pool(_ptr(x), _ptr(logits), B, HW, C, nblk, _ptr(part), _ptr(ml), _stream()), "kd_gca_pool")
+    check(lib().kd_gca_pool(_ptr(x), _ptr(logits), n_parts, B, HW, C, nblk, _ptr(part), _ptr(ml), _stream()), "kd_gca_pool")
     pooled = torch.empty((B, C), device=x.device, dtype=torch.float32)
     check(lib().kd_gca_finalize(_ptr(part), _ptr(ml), B, nblk, C, _ptr(pooled), _stream()), "kd_gca_finalize")
     _count(2)

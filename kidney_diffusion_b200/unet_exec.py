@@ -352,8 +352,10 @@ class UnetExecutor:
         a2, _ = self._gn(h, None, 1.0, P.G, P.g2, P.be2, ss)
         if exists(P.gca):
             g = P.gca
-            h2 = ops.conv_gemm(a2, P.w2, P.b2, ksize=3)
-            logits = ops.rowdot(h2, g["wk"], g["bk"])
+            h2 = ops.conv_gemm(a2, P.w2, P.b2, ksize=3, logit_w=g["wk"])
+            logits = getattr(h2, "_kd_logits", None)  # to_k from the conv epilogue (its bias cancels in the softmax)
+            if logits is None:
+                logits = ops.rowdot(h2, g["wk"], g["bk"])
             pooled = ops.gca_pool(h2, logits)
             hid = ops.linear_small(pooled, g["w0"], g["b0"], post_act=ops.ACT_SILU)
             gate = ops.linear_small(hid, g["w1"], g["b1"], post_act=ops.ACT_SIGMOID)

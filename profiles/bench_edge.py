@@ -1,0 +1,50 @@
+"""Micro-benchmark of the non-GEMM-shaped kernels of a patch-step at full size (B patches of 1024^2): CUDA-event timing of
+kd_init_conv, kd_final_conv and the global-context pair, with their algorithmic HBM bytes.  Usage: python profiles/bench_edge.py [B]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from kidney_diffusion_b200 import ops
+from kidney_diffusion_b200.build import build_library
+
+build_library()
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+S, dim, dev = 1024, 128, "cuda"
+
+
+def timeit(fn, n=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+x = torch.randn(B, 3, S, S, device=dev)
+wp = (torch.randn(dim, ops.init_conv_kp(3, 15), device=dev) * 0.05).half()
+bias = torch.randn(dim, device=dev)
+add = torch.randn(B, S, S, dim, device=dev).half()
+out = torch.empty_like(add)
+ms = timeit(lambda: ops.init_conv(x, 15, wp, bias, add, out))
+gb = (x.numel() * 4 + add.numel() * 2 + out.numel() * 2) / 1e9
+print(f"init_conv  B={B}: {ms:.3f} ms  ({gb / ms * 1e3:.0f} GB/s algorithmic, {2 * B * S * S * dim * 768 / ms / 1e9:.0f} TFLOP/s issued)")
+ms = timeit(lambda: ops.init_conv(x, 15, wp, bias, None, out))
+print(f"init_conv (no addend): {ms:.3f} ms")
+import ctypes
+L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kidney_diffusion_b200", "libkidney_b200.so"))
+for m in (1, 2, 4, 3, 5, 6, 7):
+    L.kd_exp_init_conv_debug(m)
+    print(f"  dbg mask {m} (1 = no fill, 2 = no mma, 4 = no store): {timeit(lambda: ops.init_conv(x, 15, wp, bias, None, out)):.3f} ms")
+L.kd_exp_init_conv_debug(0)
+
+w = torch.randn(3, 3, 3, dim + 3, device=dev) * 0.05
+fb = torch.randn(3, device=dev)
+ms = timeit(lambda: ops.final_conv(add, x, w, fb))
+gb = (add.numel() * 2 + 2 * x.numel() * 4) / 1e9
+print(f"final_conv B={B}: {ms:.3f} ms  ({gb / ms * 1e3:.0f} GB/s algorithmic)")

@@ -62,11 +62,12 @@ if os.environ.get("KD_OP_TABLE"):
     torch.cuda.synchronize()
     prof, ops.op_profile = ops.op_profile, None
     agg = collections.OrderedDict()
-    for name, e0, e1 in prof:
-        a = agg.setdefault(name, [0, 0.0])
+    for name, e0, e1, nbytes in prof:
+        a = agg.setdefault(name, [0, 0.0, 0])
         a[0] += 1
         a[1] += e0.elapsed_time(e1)
+        a[2] += nbytes
     tot = sum(a[1] for a in agg.values())
     print(f"op table, B={B}, S={S}: total {tot:.2f} ms ({tot / B:.2f} ms per patch-step)")
-    for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"  {name:16s} n={n:4d}  {ms:8.3f} ms  {100 * ms / tot:5.1f}%")
+    for name, (n, ms, nbytes) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"  {name:16s} n={n:4d}  {ms:8.3f} ms  {100 * ms / tot:5.1f}%   {nbytes / 1e9:7.2f} GB touched  {nbytes / ms / 1e6:6.0f} GB/s")

@@ -591,3 +591,27 @@ def test_fused_groupnorm_statistics_match_standalone(cuda_lib, B, H, W, Cin, Cou
     of = out.float().cpu().permute(0, 3, 1, 2).reshape(B, 8, -1)
     assert torch.allclose(mr[..., 0], of.mean(-1), atol=1e-4, rtol=1e-4)
     assert torch.allclose(mr[..., 1], (of.var(-1, unbiased=False) + 1e-5).rsqrt(), atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 32, 32, 128, 128, 3), (3, 8, 8, 128, 256, 3), (1, 40, 24, 64, 512, 3), (1, 128, 64, 128, 128, 3)])
+def test_fused_global_context_logits_match_rowdot(cuda_lib, B, H, W, Cin, Cout, k):
+    """GlobalContext to_k logits emitted by the conv epilogue (one partial per 64 output channels) == kd_rowdot over the
+    stored tensor, and the pooled context computed from either is the same."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(H * 7 + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = bf(torch.randn(Cout, k * k * Cin, generator=g) / math.sqrt(k * k * Cin)).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    wk = torch.randn(Cout, generator=g).to(DEV)
+    out = ops.conv_gemm(nhwc(x), w, b, ksize=k, logit_w=wk, want_stats=True)
+    parts = getattr(out, "_kd_logits", None)
+    assert parts is not None and parts.shape == (Cout // 64, B, H * W)
+    assert getattr(out, "_kd_stats", None) is not None
+    alone = ops.rowdot(out, wk, None)
+    exact = (out.double().cpu().view(B, H * W, Cout) * wk.double().cpu()).sum(-1)
+    scale = float(exact.abs().max())
+    assert float((parts.double().cpu().sum(0) - exact).abs().max()) < 1e-5 * scale + 1e-5
+    assert float((alone.double().cpu() - exact).abs().max()) < 1e-5 * scale + 1e-5
+    pa, pb = ops.gca_pool(out, parts), ops.gca_pool(out, alone)
+    assert torch.allclose(pa, pb, atol=1e-4, rtol=1e-4)
