@@ -79,10 +79,22 @@ __device__ __forceinline__ h16x8 float_to_h16x8(const float* in) {
   return o;
 }
 
-// fast intrinsics (ex2.approx / rcp.approx, <= 2 ulp): the library is built without --use_fast_math so that the sampler
-// update and the time embedding keep IEEE semantics, but activations run 4.2 G times per step
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// fast activations: the library is built without --use_fast_math so that the sampler update and the time embedding keep
+// IEEE semantics, but SiLU runs 4.2 G times per step.  Raw ex2.approx.ftz / rcp.approx.ftz (<= 2 ulp) -- __expf and
+// __fdividef carry range fix-ups (FSETP + 3 extra FMUL per element) that made the conv epilogue issue-bound.
+// Limits are exact: x -> -inf gives x * rcp(inf) = -0, x -> +inf gives x * rcp(1) = x.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -90,6 +102,19 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == KD_ACT_GELU) return gelu_f(x);
   if (act == KD_ACT_SIGMOID) return sigmoid_f(x);
   return x;
+}
+
+// 8 values at a time under ONE uniform branch per activation kind: a per-element apply_act gets if-converted by the
+// compiler (all activations computed speculatively, MUFU included, then selected) even when act == NONE
+__device__ __forceinline__ void apply_act8(float* v, int act) {
+  if (act == KD_ACT_NONE) return;
+  if (act == KD_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act);
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

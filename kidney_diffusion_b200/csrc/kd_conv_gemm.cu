@@ -185,10 +185,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (nc + g * 8 + 8 > p.Cout) break;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = __uint_as_float(acc[g * 8 + j]) + bias_smem[chunk * 32 + g * 8 + j];
-          v[j] = apply_act(v[j], p.act);
-        }
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]) + bias_smem[chunk * 32 + g * 8 + j];
+        apply_act8(v, p.act);
         if (p.addend != nullptr) {
           float a[8];
           if (p.addend_f32) {
@@ -341,7 +339,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + v[j], p.act);
+    for (int j = 0; j < 8; ++j) v[j] += __uint_as_float(acc[g * 8 + j]);
+    apply_act8(v, p.act);
     if (p.addend != nullptr) {
       float a[8];
       if (p.addend_f32) {
@@ -525,7 +524,8 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
             const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + q * 8 + 4);
             v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[q * 8 + j]) + v[j], p.act);
+            for (int j = 0; j < 8; ++j) v[j] += __uint_as_float(acc[q * 8 + j]);
+            apply_act8(v, p.act);
             const uint32_t chunk16 = (uint32_t)(half * 4 + q);
             const uint32_t dst = stage + (uint32_t)r * 128u + ((chunk16 ^ ((uint32_t)r & 7u)) << 4);
             if (p.addend != nullptr && row_ok && nc + q * 8 + 8 <= p.Cout) {

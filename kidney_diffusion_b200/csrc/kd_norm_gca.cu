@@ -149,7 +149,8 @@ __global__ void gn_apply_kernel(const h16* __restrict__ x, h16* __restrict__ y, 
       float v[8];
       h16x8_to_float(*reinterpret_cast<h16x8*>(&raw[u]), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(A[j], v[j], Bc[j]), act);
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(A[j], v[j], Bc[j]);
+      apply_act8(v, act);
       h16x8 o8 = float_to_h16x8(v);
       *reinterpret_cast<int4*>(yb + (p + (long)u * lanes) * C) = *reinterpret_cast<int4*>(&o8);
     }
@@ -159,7 +160,8 @@ __global__ void gn_apply_kernel(const h16* __restrict__ x, h16* __restrict__ y, 
     float v[8];
     h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(A[j], v[j], Bc[j]), act);
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(A[j], v[j], Bc[j]);
+    apply_act8(v, act);
     h16x8 o8 = float_to_h16x8(v);
     *reinterpret_cast<int4*>(yb + p * C) = *reinterpret_cast<int4*>(&o8);
   }
