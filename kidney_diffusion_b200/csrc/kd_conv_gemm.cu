@@ -127,16 +127,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one elected lane)
-    if (lane == 0) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + s * STAGE_BYTES;
-        const uint64_t a_desc = make_sw128_desc(a_addr);
-        const uint64_t b_desc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+    // ================================================================ MMA issuer (warp-convergent loop, one elected lane issues)
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(smem_u32(&full_bar[s]), ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+      const uint64_t a_desc = make_sw128_desc(a_addr);
+      const uint64_t b_desc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -144,8 +144,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot once these MMAs have read it
       }
-      umma_commit(smem_u32(tmem_full_bar));  // accumulator complete
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(smem_u32(tmem_full_bar));  // accumulator complete
+    __syncwarp();
   } else {
     // ================================================================ epilogue: TMEM -> registers -> global
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -722,8 +724,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (leader CTA, one lane)
-    if (rank == 0 && lane == 0) {
+    // ================================================================ MMA issuer (leader CTA): warp-convergent loop, one
+    // elected lane issues (descriptors stay in uniform registers; a lane-0-only loop cost a R2UR waterfall per MMA)
+    if (rank == 0) {
       uint32_t it = 0, tile_iter = 0;
       for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
         const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
@@ -738,12 +741,16 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint32_t a_addr = smem_base + s * STAGE_BYTES;
           const uint64_t a_desc = make_sw128_desc(a_addr);
           const uint64_t b_desc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(smem_u32(&empty_bar[s]));
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(smem_u32(&empty_bar[s]));
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
+        if (elect_one()) umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -881,8 +888,9 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (leader CTA, one lane)
-    if (rank == 0 && lane == 0) {
+    // ================================================================ MMA issuer (leader CTA): the whole warp runs the loop
+    // convergently (all lanes poll the barriers and compute the same, uniform, descriptors), one elected lane issues
+    if (rank == 0) {
       uint32_t ita = 0, itb = 0, tile_iter = 0;
       for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
         const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
@@ -895,23 +903,29 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           mbar_wait(smem_u32(&a_full[sa]), pha);
           tc_fence_after();
           const uint32_t a_stage = a_base + sa * HALO_STAGE_BYTES;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++itb) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
             const uint32_t sb = itb % BS;
             const uint32_t phb = (itb / BS) & 1;
+            ++itb;
             mbar_wait(smem_u32(&b_full[sb]), phb);
             tc_fence_after();
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint64_t a_desc = make_sw128_desc(a_stage + (uint32_t)(ky * HALO_W + kx) * 128u, HALO_W * 128);
             const uint64_t b_desc = make_sw128_desc(b_base + sb * B_HALF_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (ch | tap | k) != 0 ? 1u : 0u);
-            umma_commit_2sm(smem_u32(&b_empty[sb]));
+              for (int k = 0; k < BK / 16; ++k)
+                umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (ch | tap | k) != 0 ? 1u : 0u);
+              umma_commit_2sm(smem_u32(&b_empty[sb]));
+            }
+            __syncwarp();
           }
-          umma_commit_2sm(smem_u32(&a_empty[sa]));
+          if (elect_one()) umma_commit_2sm(smem_u32(&a_empty[sa]));
+          __syncwarp();
         }
-        umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
+        if (elect_one()) umma_commit_2sm(smem_u32(&tmem_full_bar[as]));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

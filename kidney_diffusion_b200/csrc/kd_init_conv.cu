@@ -36,7 +36,6 @@ struct InitParams {
   const float* bias;
   const h16* addend;
   h16* out;
-  int dbg;
 };
 
 template <int BN>
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     // (one thread issues ~90 MMAs per pass: all operand addresses come from wrap-around counters, no div / mod on this path)
-    if (lane == 0) {
+    {
       uint32_t cc = 0, q = 0;
       const uint64_t a_desc0 = make_nosw_desc(ring_base, 128, 128);
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -130,11 +129,12 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
             mbar_wait(smem_u32(&b_full[s]), (cc / IC_BSTAGES) & 1);
             tc_fence_after();
             const uint64_t b_desc = make_sw128_desc(smem_base + s * B_STAGE_BYTES);
+            const bool leader = elect_one();
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               if (pair < p.n_pairs) {
                 const int slot1 = (slot + 1 == p.ring) ? 0 : slot + 1;
-                if (!(p.dbg & 2)) {
+                if (leader) {
                   const uint32_t acc = pair != 0 ? 1u : 0u;
                   umma_f16(d0, a_desc0 + (uint64_t)((slot * p.C + c) * (IC_ROWC_BYTES >> 4)), b_desc + (uint64_t)(2 * t), IDESC, acc);
                   umma_f16(d0 + BN, a_desc0 + (uint64_t)((slot1 * p.C + c) * (IC_ROWC_BYTES >> 4)), b_desc + (uint64_t)(2 * t), IDESC,
@@ -147,9 +147,11 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
                 }
               }
             }
-            umma_commit(smem_u32(&b_empty[s]));
+            if (leader) umma_commit(smem_u32(&b_empty[s]));
+            __syncwarp();
           }
-          umma_commit(smem_u32(&tmem_full[a]));
+          if (elect_one()) umma_commit(smem_u32(&tmem_full[a]));
+          __syncwarp();
           s0 += 2;
           if (s0 >= p.ring) s0 -= p.ring;
         }
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
           }
           if (chunk & 1) {
             __syncwarp();
-            if (row_live && !(p.dbg & 4)) {
+            if (row_live) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int px = i * 4 + (lane >> 3), unit = lane & 7;
@@ -260,7 +262,6 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
           const int e0 = (un >> 3) * 8 + (un & 7);
           const int gy = r0 + rr - pad;
           float v[8];
-          if (p.dbg & 1) continue;
           if (gy >= 0 && gy < p.H) {
             const float* src = img + ((long long)c * p.H + gy) * p.W;
 #pragma unroll
@@ -307,9 +308,6 @@ int launch_init(const CUtensorMap& mw, const InitParams& p, cudaStream_t stream)
 
 }  // namespace
 
-static int g_init_dbg = 0;
-extern "C" int kd_exp_init_conv_debug(int m) { g_init_dbg = m; return 0; }
-
 extern "C" int kd_init_conv_kp(int C, int ksize) { return ((ksize * C * 16 + 63) / 64) * 64; }
 
 extern "C" int kd_init_conv(const float* x, int B, int C, int H, int W, int ksize, const void* w_packed, const float* bias,
@@ -333,7 +331,6 @@ extern "C" int kd_init_conv(const float* x, int B, int C, int H, int W, int ksiz
   p.n_chunks = kd_ceil_div(p.n_pairs, 4);
   p.ring = ksize + 3;
   p.bias = bias;
-  p.dbg = g_init_dbg;
   p.addend = reinterpret_cast<const h16*>(addend);
   p.out = reinterpret_cast<h16*>(out);
   CUtensorMap mw;

@@ -36,12 +36,6 @@ gb = (x.numel() * 4 + add.numel() * 2 + out.numel() * 2) / 1e9
 print(f"init_conv  B={B}: {ms:.3f} ms  ({gb / ms * 1e3:.0f} GB/s algorithmic, {2 * B * S * S * dim * 768 / ms / 1e9:.0f} TFLOP/s issued)")
 ms = timeit(lambda: ops.init_conv(x, 15, wp, bias, None, out))
 print(f"init_conv (no addend): {ms:.3f} ms")
-import ctypes
-L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kidney_diffusion_b200", "libkidney_b200.so"))
-for m in (1, 2, 4, 3, 5, 6, 7):
-    L.kd_exp_init_conv_debug(m)
-    print(f"  dbg mask {m} (1 = no fill, 2 = no mma, 4 = no store): {timeit(lambda: ops.init_conv(x, 15, wp, bias, None, out)):.3f} ms")
-L.kd_exp_init_conv_debug(0)
 
 w = torch.randn(3, 3, 3, dim + 3, device=dev) * 0.05
 fb = torch.randn(3, device=dev)
