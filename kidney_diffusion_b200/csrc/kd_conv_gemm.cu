@@ -782,7 +782,10 @@ constexpr int HALO_BYTES = HALO_H * HALO_W * 128;                 // 23 040 B ac
 constexpr int HALO_STAGE_BYTES = ((HALO_BYTES + 1023) / 1024) * 1024;  // stage stride keeps 1024-byte alignment
 constexpr int HALO_AS = 3;
 
-template <int BN, int BS, bool TADD>
+// TPS = taps per B-ring stage: with BN = 128 one MMA is only 64 tensor-pipe cycles, and a barrier wait + commit per tap
+// (4 MMAs) left the issuing warp, not the pipe, as the limit (ncu: pipe 52 % active, no barrier ever spun); three taps per
+// stage amortise that over 12 MMAs.
+template <int BN, int BS, bool TADD, int TPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
@@ -797,8 +800,9 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + HALO_AS * HALO_STAGE_BYTES;
   constexpr int EPI_BUFS = TADD ? 4 : 2;
-  const uint32_t epi_smem = b_base + BS * B_HALF_BYTES;
-  uint8_t* ctrl = smem_gen + HALO_AS * HALO_STAGE_BYTES + BS * B_HALF_BYTES + EPI_BUFS * EPI_STAGE_BYTES;
+  constexpr int B_STAGE = TPS * B_HALF_BYTES;
+  const uint32_t epi_smem = b_base + BS * B_STAGE;
+  uint8_t* ctrl = smem_gen + HALO_AS * HALO_STAGE_BYTES + BS * B_STAGE + EPI_BUFS * EPI_STAGE_BYTES;
   uint64_t* add_bar = reinterpret_cast<uint64_t*>(ctrl + 320);
   float* epi_aux = reinterpret_cast<float*>(ctrl + 384);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
@@ -875,13 +879,16 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           tma_load_5d_2sm(a_base + sa * HALO_STAGE_BYTES, map, fa_local & kPeerBitMask, c0, w0 - 1, h0 - 1, tile_b, 0);
           if (rank != 0) mbar_remote_arrive(fa_local, 0);
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++itb) {
+          for (int tg = 0; tg < 9 / TPS; ++tg, ++itb) {
             const uint32_t sb = itb % BS;
             const uint32_t phb = (itb / BS) & 1;
             mbar_wait(smem_u32(&b_empty[sb]), phb ^ 1u);
             const uint32_t fb_local = smem_u32(&b_full[sb]);
-            if (rank == 0) mbar_expect_tx(fb_local, 2 * B_HALF_BYTES);
-            tma_load_2d_2sm(b_base + sb * B_HALF_BYTES, &map_w, fb_local & kPeerBitMask, tap * Ctot + ch * BK, n0);
+            if (rank == 0) mbar_expect_tx(fb_local, 2 * B_STAGE);
+#pragma unroll
+            for (int j = 0; j < TPS; ++j)
+              tma_load_2d_2sm(b_base + sb * B_STAGE + j * B_HALF_BYTES, &map_w, fb_local & kPeerBitMask,
+                              (tg * TPS + j) * Ctot + ch * BK, n0);
             if (rank != 0) mbar_remote_arrive(fb_local, 0);
           }
         }
@@ -904,19 +911,23 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           tc_fence_after();
           const uint32_t a_stage = a_base + sa * HALO_STAGE_BYTES;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tg = 0; tg < 9 / TPS; ++tg) {
             const uint32_t sb = itb % BS;
             const uint32_t phb = (itb / BS) & 1;
             ++itb;
             mbar_wait(smem_u32(&b_full[sb]), phb);
             tc_fence_after();
-            const int ky = tap / 3, kx = tap - ky * 3;
-            const uint64_t a_desc = make_sw128_desc(a_stage + (uint32_t)(ky * HALO_W + kx) * 128u, HALO_W * 128);
-            const uint64_t b_desc = make_sw128_desc(b_base + sb * B_HALF_BYTES);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (ch | tap | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < TPS; ++j) {
+                const int tap = tg * TPS + j;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint64_t a_desc = make_sw128_desc(a_stage + (uint32_t)(ky * HALO_W + kx) * 128u, HALO_W * 128);
+                const uint64_t b_desc = make_sw128_desc(b_base + sb * B_STAGE + j * B_HALF_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (ch | tap | k) != 0 ? 1u : 0u);
+              }
               umma_commit_2sm(smem_u32(&b_empty[sb]));
             }
             __syncwarp();
@@ -1081,9 +1092,9 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   return KD_OK;
 }
 
-template <int BN, int BS, bool TADD>
+template <int BN, int BS, bool TADD, int TPS>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
-  constexpr int SMEM = HALO_AS * HALO_STAGE_BYTES + BS * (BN / 2) * BK * 2 + (TADD ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 384 +
+  constexpr int SMEM = HALO_AS * HALO_STAGE_BYTES + BS * TPS * (BN / 2) * BK * 2 + (TADD ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 384 +
                        3 * BN * 4;
   static_assert(SMEM <= 232448, "halo kernel exceeds the 227 KB shared-memory limit");
   CUtensorMap mo, madd;
@@ -1099,7 +1110,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   {
     std::lock_guard<std::mutex> lock(mu);
     if (!configured) {
-      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, BS, TADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, BS, TADD, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured = true;
     }
   }
@@ -1108,7 +1119,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
   int clusters = kd_num_sms() / 2;
   if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_halo_kernel<BN, BS, TADD><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
+  conv_gemm_halo_kernel<BN, BS, TADD, TPS><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -1258,11 +1269,11 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
   const bool tadd = use_pair && addend != nullptr && !d->addend_f32 && !d->out_f32 && d->out_mode == 0;
   if (use_halo) {
     if (tadd) {
-      if (BN == 256) return launch_halo<256, 5, true>(ma, mb, mw, p, stream);
-      return launch_halo<128, 8, true>(ma, mb, mw, p, stream);
+      if (BN == 256) return launch_halo<256, 5, true, 1>(ma, mb, mw, p, stream);
+      return launch_halo<128, 3, true, 3>(ma, mb, mw, p, stream);
     }
-    if (BN == 256) return launch_halo<256, 7, false>(ma, mb, mw, p, stream);
-    return launch_halo<128, 10, false>(ma, mb, mw, p, stream);
+    if (BN == 256) return launch_halo<256, 7, false, 1>(ma, mb, mw, p, stream);
+    return launch_halo<128, 4, false, 3>(ma, mb, mw, p, stream);
   }
   if (use_pair) {
     if (tadd) {
