@@ -82,18 +82,26 @@ int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
                  const void* addend /* or NULL */, const float* addend_scale /* [B,Cout] or NULL (=1) */, void* out,
                  kd_stream_t stream);
 
-/* kd_conv_gemm whose epilogue additionally emits, for the consumers of the stored output,
- *   stats      : fused GroupNorm statistics, stats[row][Cout/8] = {sum, sumsq} (fp32) over 32 output pixels x 8 channels,
- *                rows = 4 per 128-pixel M-tile.  kd_conv_stats_layout gives the buffer geometry for a descriptor (layout[0] =
- *                rows, 0 if this shape cannot produce fused outputs; [1] = M-tiles per batch group; [2] = batch images per
- *                tile), consumed by kd_oct_reduce;
- *   logit_parts: the GlobalContext to_k 1x1 conv (replaces kd_rowdot): logit_parts[g][b*H*W + n] = sum over the 64 output
- *                channels of group g of out[b,n,c] * logit_w[c]; kd_gca_pool adds the Cout/64 parts in fixed order.
- * Either may be NULL; both need layout[0] > 0; logits also need out_mode 0, Cout % 64 == 0 and no addend_scale. */
-int kd_conv_stats_layout(const KdConvDesc* desc, int* layout /* [3] */);
+/* Operator fusion around kd_conv_gemm (every pointer may be NULL):
+ *   stats      : OUT, fused GroupNorm statistics of the stored output, stats[row][Cout/8] = {sum, sumsq} (fp32) over 32 output
+ *                pixels x 8 channels, rows = 4 per 128-pixel M-tile; geometry from kd_conv_stats_layout, consumed by kd_oct_reduce;
+ *   logit_w / logit_parts : the GlobalContext to_k 1x1 conv (replaces kd_rowdot): logit_parts[g][b*H*W + n] = sum over the
+ *                64 output channels of group g of out[b,n,c] * logit_w[c]; kd_gca_pool adds the Cout/64 parts in fixed order
+ *                (needs out_mode 0, Cout % 64 == 0, no addend_scale);
+ *   pre_coef   : IN, [B][Ca+Cb] x {A, B} fp32 from kd_gn_finalize_oct: the convolution consumes SiLU(A * x + B) instead of
+ *                x -- GroupNorm + scale/shift + SiLU of Block.forward applied to the raw tensors while the halo tile sits in
+ *                shared memory (replaces kd_gn_apply and its write + re-read of the activated tensor).
+ * kd_conv_stats_layout: layout[0] = rows of the stats buffer, 0 if this shape's kernel cannot produce stats / logits;
+ * [1] = M-tiles per batch group; [2] = batch images per tile; [3] = 1 if pre_coef is supported (3x3 halo kernel). */
+typedef struct KdConvFusion {
+  float* stats;
+  const float* logit_w;
+  float* logit_parts;
+  const float* pre_coef;
+} KdConvFusion;
+int kd_conv_stats_layout(const KdConvDesc* desc, int* layout /* [4] */);
 int kd_conv_gemm_fused(const KdConvDesc* desc, const void* xa, const void* xb, const void* w, const float* bias, const void* addend,
-                       const float* addend_scale, void* out, float* stats, const float* logit_w, float* logit_parts,
-                       kd_stream_t stream);
+                       const float* addend_scale, void* out, const KdConvFusion* fusion, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ small-M linear (time / conditioning towers, GCA MLP)
  * replaces: nn.Linear on (B, features) tensors: to_time_hiddens, to_time_cond, to_time_tokens, ResnetBlock.time_mlp,
@@ -128,12 +136,16 @@ int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_offset, int
  * kd_oct_reduce: first-level sum of partial rows into out[b][NS][C/8][2], NS = kd_oct_reduce_splits(rpt, tiles, TB); physical
  *                row of logical (b, i): tile_b = b / TB, sub = b % TB, rpb = rpt / TB,
  *                row = ((tile_b * tiles + i / rpb) * rpt) + sub * rpb + i % rpb, for i < tiles * rpb  (conv: rpt = 4).
- * kd_gn_finalize_oct: mean / rstd per (b, group) from the split sums of one or two (concatenated) sources. */
+ * kd_gn_finalize_oct: mean / rstd per (b, group) from the split sums of one or two (concatenated) sources; with coef != NULL
+ *                also the per-channel affine coef[b][c] = {A, B} of GroupNorm + (scale+1, shift) on the RAW sources
+ *                (y = A*x + B; source scales folded into A), input of KdConvFusion.pre_coef. */
 int kd_oct_stats(const void* x, int B, long HW, int C, float* partial /* [B][nblk][C/8][2] */, int nblk, kd_stream_t stream);
 int kd_oct_reduce_splits(int rpt, int tiles, int TB);
 int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, int B, int n_oct, float* out /* [B][NS][n_oct][2] */, kd_stream_t stream);
 int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, float scale_a, const float* sum_b, int n_oct_b, int ns_b, float scale_b,
-                       int B, int num_groups, int group_size, double count, float eps, float* mean_rstd, kd_stream_t stream);
+                       int B, int num_groups, int group_size, double count, float eps, float* mean_rstd,
+                       const float* gamma /* [C] */, const float* beta, const float* scale_shift /* [B][ss_stride]: scale | shift, or NULL */,
+                       long ss_stride, float* coef /* [B][C][2] or NULL */, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ K4: GlobalContext gate
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */

@@ -24,6 +24,10 @@ class KdConvDesc(Structure):
     ]
 
 
+class KdConvFusion(Structure):
+    _fields_ = [("stats", c_void_p), ("logit_w", c_void_p), ("logit_parts", c_void_p), ("pre_coef", c_void_p)]
+
+
 _P = c_void_p
 _F = c_float
 _I = c_int
@@ -37,7 +41,7 @@ SIGNATURES = {
     "kd_set_conv_impl": (c_int, [_I]),
     "kd_conv_gemm": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "kd_conv_stats_layout": (c_int, [POINTER(KdConvDesc), POINTER(c_int)]),
-    "kd_conv_gemm_fused": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "kd_conv_gemm_fused": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, POINTER(KdConvFusion), _P]),
     "kd_linear_small": (c_int, [_P, _I, _I, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
     "kd_sinu_emb": (c_int, [_P, _P, _I, _I, _P, _P]),
     "kd_gn_stats": (c_int, [_P, _I, _L, _I, _I, _I, _I, _P, _I, _P]),
@@ -51,7 +55,7 @@ SIGNATURES = {
     "kd_oct_stats": (c_int, [_P, _I, _L, _I, _P, _I, _P]),
     "kd_oct_reduce": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "kd_oct_reduce_splits": (c_int, [_I, _I, _I]),
-    "kd_gn_finalize_oct": (c_int, [_P, _I, _I, _F, _P, _I, _I, _F, _I, _I, _I, c_double, _F, _P, _P]),
+    "kd_gn_finalize_oct": (c_int, [_P, _I, _I, _F, _P, _I, _I, _F, _I, _I, _I, c_double, _F, _P, _P, _P, _P, _L, _P, _P]),
     "kd_layernorm_h16": (c_int, [_P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_layernorm_f32": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_kv_assemble": (c_int, [_P, _L, _I, _P, _I, _P, _P, _I, _I, _P]),

@@ -37,6 +37,7 @@ struct ConvParams {
   float* stats;  // optional per-(row group, channel octet) {sum, sumsq} of the stored output (fused GroupNorm statistics)
   const float* logit_w;  // optional GlobalContext to_k weight [Cout]: the epilogue also emits per-pixel partial dot products
   float* logit_parts;    // [Cout / 64][B*H*W] fp32, one partial per 64-column group (summed in fixed order by kd_gca_pool)
+  const float2* pre_coef;  // optional [B][Ca+Cb] {A, B}: the A operand becomes SiLU(A * x + B) (fused GroupNorm apply, halo kernel)
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -776,17 +777,19 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 // tcgen05.mma read (verified on B200 by profiles/halo_probe.py: rel-L2 7e-7).  L2 -> SMEM traffic per k-block drops from
 // 16 KB (A) + B to 2.5 KB + B, which is what bounded the tap-loop kernel (profiles/README.md).
 //
-// Two operand rings: A halo tiles (HALO_AS stages, one per 64-channel chunk) and weight tiles (BS stages, one per tap).
+// Two operand rings: A halo tiles (AS stages, one per 64-channel chunk) and weight tiles (BS stages, one per tap).
 constexpr int HALO_TW = 8, HALO_TH = 16, HALO_W = HALO_TW + 2, HALO_H = HALO_TH + 2;
 constexpr int HALO_BYTES = HALO_H * HALO_W * 128;                 // 23 040 B actually transferred per chunk
 constexpr int HALO_STAGE_BYTES = ((HALO_BYTES + 1023) / 1024) * 1024;  // stage stride keeps 1024-byte alignment
-constexpr int HALO_AS = 3;
 
 // TPS = taps per B-ring stage: with BN = 128 one MMA is only 64 tensor-pipe cycles, and a barrier wait + commit per tap
 // (4 MMAs) left the issuing warp, not the pipe, as the limit (ncu: pipe 52 % active, no barrier ever spun); three taps per
 // stage amortise that over 12 MMAs.
-template <int BN, int BS, bool TADD, int TPS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+// PRE: GroupNorm + scale/shift + SiLU of the consuming Block applied to the halo tile in shared memory (4 extra warps
+// 12..15 per CTA: a_full -> transform in place -> a_ready -> MMA), so the activated tensor never exists in HBM.
+constexpr int NUM_THREADS3 = 512;
+template <int BN, int AS, int BS, bool TADD, int TPS, bool PRE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PRE ? NUM_THREADS3 : NUM_THREADS2, 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
                       const __grid_constant__ CUtensorMap map_add, const ConvParams p, const int num_pair_tiles) {
@@ -798,21 +801,22 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + HALO_AS * HALO_STAGE_BYTES;
+  const uint32_t b_base = smem_base + AS * HALO_STAGE_BYTES;
   constexpr int EPI_BUFS = TADD ? 4 : 2;
   constexpr int B_STAGE = TPS * B_HALF_BYTES;
   const uint32_t epi_smem = b_base + BS * B_STAGE;
-  uint8_t* ctrl = smem_gen + HALO_AS * HALO_STAGE_BYTES + BS * B_STAGE + EPI_BUFS * EPI_STAGE_BYTES;
+  uint8_t* ctrl = smem_gen + AS * HALO_STAGE_BYTES + BS * B_STAGE + EPI_BUFS * EPI_STAGE_BYTES;
   uint64_t* add_bar = reinterpret_cast<uint64_t*>(ctrl + 320);
+  uint64_t* a_ready = reinterpret_cast<uint64_t*>(ctrl + 352);  // PRE: leader only, 4 transform warps x 2 CTAs
   float* epi_aux = reinterpret_cast<float*>(ctrl + 384);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
-  uint64_t* a_empty = a_full + HALO_AS;
-  uint64_t* b_full = a_empty + HALO_AS;
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* b_full = a_empty + AS;
   uint64_t* b_empty = b_full + BS;
   uint64_t* tmem_full_bar = b_empty + BS;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  static_assert((2 * HALO_AS + 2 * BS + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+  static_assert((2 * AS + 2 * BS + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -831,9 +835,10 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
   if (warp == 1 && lane == 0) {
 #pragma unroll
-    for (int s = 0; s < HALO_AS; ++s) {
-      mbar_init(smem_u32(&a_full[s]), 2);
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(smem_u32(&a_full[s]), PRE ? 1 : 2);  // PRE: each CTA tracks its own halo tile (its transform warps wait on it)
       mbar_init(smem_u32(&a_empty[s]), 1);
+      mbar_init(smem_u32(&a_ready[s]), 8);
     }
 #pragma unroll
     for (int s = 0; s < BS; ++s) {
@@ -855,29 +860,12 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ================================================================ TMA producer (both CTAs, one lane each)
+    // ================================================================ weight (B) TMA producer (both CTAs, one lane each)
     if (lane == 0) {
-      uint32_t ita = 0, itb = 0;
+      uint32_t itb = 0;
       for (int t = cluster_id; t < num_pair_tiles; t += num_clusters) {
-        const int n_tile = t % p.n_tiles;
-        int m_tile = (t / p.n_tiles) * 2 + (int)rank;
-        const int tile_w = m_tile % p.tiles_w;
-        m_tile /= p.tiles_w;
-        const int tile_h = m_tile % p.tiles_h;
-        const int tile_b = m_tile / p.tiles_h;
-        const int w0 = tile_w * HALO_TW, h0 = tile_h * HALO_TH;
-        const int n0 = n_tile * BN + (int)rank * (BN / 2);
-        for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
-          const uint32_t sa = ita % HALO_AS;
-          const uint32_t pha = (ita / HALO_AS) & 1;
-          mbar_wait(smem_u32(&a_empty[sa]), pha ^ 1u);
-          const uint32_t fa_local = smem_u32(&a_full[sa]);
-          if (rank == 0) mbar_expect_tx(fa_local, 2 * HALO_BYTES);
-          const bool src_b = ch >= p.chunks_a;
-          const CUtensorMap* map = src_b ? &map_b : &map_a;
-          const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
-          tma_load_5d_2sm(a_base + sa * HALO_STAGE_BYTES, map, fa_local & kPeerBitMask, c0, w0 - 1, h0 - 1, tile_b, 0);
-          if (rank != 0) mbar_remote_arrive(fa_local, 0);
+        const int n0 = (t % p.n_tiles) * BN + (int)rank * (BN / 2);
+        for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
 #pragma unroll 1
           for (int tg = 0; tg < 9 / TPS; ++tg, ++itb) {
             const uint32_t sb = itb % BS;
@@ -894,6 +882,38 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
       }
     }
+  } else if (warp == 3) {
+    // ================================================================ halo (A) TMA producer: its own warp, so the A ring runs
+    // AS chunks ahead of the MMA independently of the weight ring (the fused pre-activation adds a transform stage to the
+    // A pipeline, which a load issued only after the previous chunk's nine weight loads could not hide)
+    if (lane == 0) {
+      uint32_t ita = 0;
+      for (int t = cluster_id; t < num_pair_tiles; t += num_clusters) {
+        int m_tile = (t / p.n_tiles) * 2 + (int)rank;
+        const int tile_w = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int tile_h = m_tile % p.tiles_h;
+        const int tile_b = m_tile / p.tiles_h;
+        const int w0 = tile_w * HALO_TW, h0 = tile_h * HALO_TH;
+        for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
+          const uint32_t sa = ita % AS;
+          const uint32_t pha = (ita / AS) & 1;
+          mbar_wait(smem_u32(&a_empty[sa]), pha ^ 1u);
+          const uint32_t fa_local = smem_u32(&a_full[sa]);
+          const bool src_b = ch >= p.chunks_a;
+          const CUtensorMap* map = src_b ? &map_b : &map_a;
+          const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
+          if (PRE) {
+            mbar_expect_tx(fa_local, HALO_BYTES);
+            tma_load_5d(a_base + sa * HALO_STAGE_BYTES, map, fa_local, c0, w0 - 1, h0 - 1, tile_b, 0);
+          } else {
+            if (rank == 0) mbar_expect_tx(fa_local, 2 * HALO_BYTES);
+            tma_load_5d_2sm(a_base + sa * HALO_STAGE_BYTES, map, fa_local & kPeerBitMask, c0, w0 - 1, h0 - 1, tile_b, 0);
+            if (rank != 0) mbar_remote_arrive(fa_local, 0);
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA): the whole warp runs the loop
     // convergently (all lanes poll the barriers and compute the same, uniform, descriptors), one elected lane issues
@@ -905,9 +925,9 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
-          const uint32_t sa = ita % HALO_AS;
-          const uint32_t pha = (ita / HALO_AS) & 1;
-          mbar_wait(smem_u32(&a_full[sa]), pha);
+          const uint32_t sa = ita % AS;
+          const uint32_t pha = (ita / AS) & 1;
+          mbar_wait(smem_u32(PRE ? &a_ready[sa] : &a_full[sa]), pha);
           tc_fence_after();
           const uint32_t a_stage = a_base + sa * HALO_STAGE_BYTES;
 #pragma unroll
@@ -939,9 +959,97 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     pair_epilogue_role<BN, TADD>(p, &map_out, &map_add, add_bar, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, epi_aux, warp, lane, rank, cluster_id,
                            num_clusters, num_pair_tiles);
+  } else if (PRE && warp >= 12) {
+    // ================================================================ pre-activation transform (both CTAs, 128 threads)
+    // thread -> one physical 16-byte unit column (8 channels) and rows rbase + 16 i of the 180-row halo tile.  The 128B
+    // swizzle XORs the unit index with (row & 7), and (rbase + 16 i) & 7 is constant, so every thread's 8 channels -- and its
+    // 8 {A, B} coefficient pairs -- are fixed for the whole chunk.
+    const int tt = threadIdx.x - 384;
+    const int pu = tt & 7, rbase = tt >> 3;
+    const int lu = pu ^ (rbase & 7);  // logical channel octet of this thread
+    uint32_t ita = 0;
+    for (int t = cluster_id; t < num_pair_tiles; t += num_clusters) {
+      int m_tile = (t / p.n_tiles) * 2 + (int)rank;
+      const int tile_w = m_tile % p.tiles_w;
+      m_tile /= p.tiles_w;
+      const int tile_h = m_tile % p.tiles_h;
+      const int tile_b = m_tile / p.tiles_h;
+      const int x0 = tile_w * HALO_TW - 1, y0 = tile_h * HALO_TH - 1;
+      const bool live = tile_b < p.B;
+      for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
+        const uint32_t sa = ita % AS;
+        const uint32_t pha = (ita / AS) & 1;
+        float4 cf[4];
+        if (live) {
+          const float4* cp = reinterpret_cast<const float4*>(p.pre_coef + (long long)tile_b * Ctot + ch * BK + lu * 8);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cf[j] = __ldg(cp + j);  // {A0, B0, A1, B1} ...; halved: the SiLU below takes (A x + B) / 2
+            cf[j].x *= 0.5f; cf[j].y *= 0.5f; cf[j].z *= 0.5f; cf[j].w *= 0.5f;
+          }
+        }
+        mbar_wait(smem_u32(&a_full[sa]), pha);
+        if (live) {
+          const uint32_t col = a_base + sa * HALO_STAGE_BYTES + (uint32_t)pu * 16u;
+          // three units per step, all loads first: 24 independent FMA -> SiLU chains keep the MUFU pipe busy (one unit at a
+          // time left the warp latency-bound at ~550 cycles per unit instead of the 128-cycle MUFU issue cost)
+          constexpr int UNR = 3, ROWS = HALO_H * HALO_W;
+          static_assert(((ROWS + 15) / 16) % UNR == 0, "unit loop must split evenly");
+#pragma unroll 1
+          for (int i0 = 0; i0 < (ROWS + 15) / 16; i0 += UNR) {
+            int4 raw[UNR];
+            bool ok[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const int r = rbase + 16 * (i0 + u);
+              const int hy = r / HALO_W, hx = r - hy * HALO_W;
+              const int y = y0 + hy, x = x0 + hx;
+              // rows past the tile and zero padding of the ACTIVATED tensor (pixels outside the image) stay untouched
+              ok[u] = (r < ROWS) && y >= 0 && y < p.H && x >= 0 && x < p.W;
+              raw[u] = make_int4(0, 0, 0, 0);
+              if (ok[u]) {
+                const uint32_t addr = col + (uint32_t)r * 128u;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(raw[u].x), "=r"(raw[u].y), "=r"(raw[u].z), "=r"(raw[u].w)
+                             : "r"(addr));
+              }
+            }
+            float v[UNR][8];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              h16x8_to_float(*reinterpret_cast<const h16x8*>(&raw[u]), v[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[u][2 * j] = fmaf(cf[j].x, v[u][2 * j], cf[j].y);
+                v[u][2 * j + 1] = fmaf(cf[j].z, v[u][2 * j + 1], cf[j].w);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[u][j] = silu_from_half_arg(v[u][j]);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              if (ok[u]) {
+                const int r = rbase + 16 * (i0 + u);
+                const uint32_t addr = col + (uint32_t)r * 128u;
+                const h16x8 o8 = float_to_h16x8(v[u]);
+                const int4 ov = *reinterpret_cast<const int4*>(&o8);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ov.x), "r"(ov.y), "r"(ov.z), "r"(ov.w)
+                             : "memory");
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_remote_arrive(smem_u32(&a_ready[sa]), 0);
+      }
+    }
   }
 
   tc_fence_before();
@@ -1092,9 +1200,9 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   return KD_OK;
 }
 
-template <int BN, int BS, bool TADD, int TPS>
+template <int BN, int AS, int BS, bool TADD, int TPS, bool PRE>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream) {
-  constexpr int SMEM = HALO_AS * HALO_STAGE_BYTES + BS * TPS * (BN / 2) * BK * 2 + (TADD ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 384 +
+  constexpr int SMEM = AS * HALO_STAGE_BYTES + BS * TPS * (BN / 2) * BK * 2 + (TADD ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 384 +
                        3 * BN * 4;
   static_assert(SMEM <= 232448, "halo kernel exceeds the 227 KB shared-memory limit");
   CUtensorMap mo, madd;
@@ -1110,7 +1218,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   {
     std::lock_guard<std::mutex> lock(mu);
     if (!configured) {
-      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, BS, TADD, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BN, AS, BS, TADD, TPS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured = true;
     }
   }
@@ -1119,7 +1227,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
   int clusters = kd_num_sms() / 2;
   if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_halo_kernel<BN, BS, TADD, TPS><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
+  conv_gemm_halo_kernel<BN, AS, BS, TADD, TPS, PRE><<<2 * clusters, PRE ? NUM_THREADS3 : NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }
@@ -1172,6 +1280,7 @@ extern "C" int kd_conv_stats_layout(const KdConvDesc* d, int* layout) {
   KD_REQUIRE(d && layout, "kd_conv_stats_layout: null argument");
   const Tiling t = choose_tiling(d);
   layout[0] = layout[1] = layout[2] = 0;
+  layout[3] = t.use_halo ? 1 : 0;
   if (!t.use_pair || d->out_f32 || d->out_mode != 0 || t.TB > 2 || d->Cout % 8 != 0) return KD_OK;
   layout[0] = t.tiles_w * t.tiles_h * t.tiles_b * 4;
   layout[1] = t.tiles_w * t.tiles_h;
@@ -1181,13 +1290,17 @@ extern "C" int kd_conv_stats_layout(const KdConvDesc* d, int* layout) {
 
 extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
                             const void* addend, const float* addend_scale, void* out, kd_stream_t stream_) {
-  return kd_conv_gemm_fused(d, xa, xb, w, bias, addend, addend_scale, out, nullptr, nullptr, nullptr, stream_);
+  return kd_conv_gemm_fused(d, xa, xb, w, bias, addend, addend_scale, out, nullptr, stream_);
 }
 
 extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
-                                  const void* addend, const float* addend_scale, void* out, float* stats, const float* logit_w,
-                                  float* logit_parts, kd_stream_t stream_) {
+                                  const void* addend, const float* addend_scale, void* out, const KdConvFusion* fusion,
+                                  kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  float* stats = fusion ? fusion->stats : nullptr;
+  const float* logit_w = fusion ? fusion->logit_w : nullptr;
+  float* logit_parts = fusion ? fusion->logit_parts : nullptr;
+  const float* pre_coef = fusion ? fusion->pre_coef : nullptr;
   KD_REQUIRE(d && xa && w && out, "kd_conv_gemm: null argument");
   KD_REQUIRE(d->mode >= 0 && d->mode <= 2, "kd_conv_gemm: bad mode %d", d->mode);
   KD_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "kd_conv_gemm: bad output shape %dx%dx%d", d->B, d->H, d->W);
@@ -1219,6 +1332,7 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
   p.chunks_per_tap = (d->Ca + d->Cb) / BK;
   p.num_kb = taps * p.chunks_per_tap;
   p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out; p.stats = stats; p.logit_w = logit_w; p.logit_parts = logit_parts;
+  p.pre_coef = reinterpret_cast<const float2*>(pre_coef);
 
   // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel;
   // 3x3 convolutions on images of at least 16 x 8 pixels use the halo-reuse variant (impl 4 forces the tap-loop pair kernel)
@@ -1259,8 +1373,9 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
     rc = encode_map(&mw, w, 2, dims, str, box);
     if (rc) return rc;
   }
+  KD_REQUIRE(pre_coef == nullptr || use_halo, "kd_conv_gemm_fused: pre_coef needs the 3x3 halo kernel (kd_conv_stats_layout[3])");
   if (stats != nullptr || logit_w != nullptr) {
-    int lay[3];
+    int lay[4];
     kd_conv_stats_layout(d, lay);
     KD_REQUIRE(lay[0] > 0, "kd_conv_gemm_fused: this shape / kernel does not produce fused statistics (see kd_conv_stats_layout)");
     KD_REQUIRE(logit_w == nullptr || (logit_parts != nullptr && addend_scale == nullptr && d->Cout % 64 == 0),
@@ -1268,12 +1383,21 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
   }
   const bool tadd = use_pair && addend != nullptr && !d->addend_f32 && !d->out_f32 && d->out_mode == 0;
   if (use_halo) {
-    if (tadd) {
-      if (BN == 256) return launch_halo<256, 5, true, 1>(ma, mb, mw, p, stream);
-      return launch_halo<128, 3, true, 3>(ma, mb, mw, p, stream);
+    // <BN, A stages, B stages, TMA addend, taps per B stage, fused pre-activation>; smem: A 23 KB / stage, B 8 (16) KB / tap
+    if (p.pre_coef != nullptr) {
+      if (tadd) {
+        if (BN == 256) return launch_halo<256, 3, 5, true, 1, true>(ma, mb, mw, p, stream);
+        return launch_halo<128, 4, 2, true, 3, true>(ma, mb, mw, p, stream);
+      }
+      if (BN == 256) return launch_halo<256, 3, 7, false, 1, true>(ma, mb, mw, p, stream);
+      return launch_halo<128, 4, 4, false, 3, true>(ma, mb, mw, p, stream);
     }
-    if (BN == 256) return launch_halo<256, 7, false, 1>(ma, mb, mw, p, stream);
-    return launch_halo<128, 4, false, 3>(ma, mb, mw, p, stream);
+    if (tadd) {
+      if (BN == 256) return launch_halo<256, 3, 5, true, 1, false>(ma, mb, mw, p, stream);
+      return launch_halo<128, 3, 3, true, 3, false>(ma, mb, mw, p, stream);
+    }
+    if (BN == 256) return launch_halo<256, 3, 7, false, 1, false>(ma, mb, mw, p, stream);
+    return launch_halo<128, 3, 4, false, 3, false>(ma, mb, mw, p, stream);
   }
   if (use_pair) {
     if (tadd) {

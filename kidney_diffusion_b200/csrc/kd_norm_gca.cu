@@ -473,7 +473,9 @@ __global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, in
 // mean / rstd per (b, group) from reduced octet sums of up to two concatenated sources: one warp per group
 __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int nsa, float scale_a, const float* __restrict__ sb, int nb,
                                        int nsb, float scale_b, int G, int group_size, double count, float eps,
-                                       float* __restrict__ mean_rstd) {
+                                       float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ scale_shift, long ss_stride,
+                                       float2* __restrict__ coef) {
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
@@ -499,12 +501,29 @@ __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int
     s += __shfl_xor_sync(0xffffffffu, s, off);
     ss += __shfl_xor_sync(0xffffffffu, ss, off);
   }
+  const double mean_d = s / count;
+  double var = ss / count - mean_d * mean_d;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)eps));  // identical in every lane
   if (lane == 0) {
-    const double mean = s / count;
-    double var = ss / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mean_rstd[((long)b * G + g) * 2] = (float)mean;
-    mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    mean_rstd[((long)b * G + g) * 2] = mean;
+    mean_rstd[((long)b * G + g) * 2 + 1] = rstd;
+  }
+  if (coef != nullptr) {
+    // per-channel affine of GroupNorm (+ time scale/shift) on the RAW source tensors: y = A * x + B, same arithmetic as
+    // gn_apply_kernel; consumed by the convolution's fused pre-activation (kd_conv_gemm_fused pre_coef)
+    const int Ctot = (na + nb) * 8, Ca = na * 8;
+    for (int c = g * group_size + lane; c < (g + 1) * group_size; c += 32) {
+      const float ga = gamma[c], be = beta[c];
+      float a = rstd * ga, cc = be - mean * rstd * ga;
+      if (scale_shift != nullptr) {
+        const float sc = scale_shift[(long)b * ss_stride + c] + 1.0f;
+        const float sh = scale_shift[(long)b * ss_stride + Ctot + c];
+        a *= sc;
+        cc = cc * sc + sh;
+      }
+      coef[(long)b * Ctot + c] = make_float2(a * (c < Ca ? scale_a : scale_b), cc);
+    }
   }
 }
 
@@ -717,12 +736,15 @@ extern "C" int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, i
 
 extern "C" int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, float scale_a, const float* sum_b, int n_oct_b, int ns_b,
                                   float scale_b, int B, int num_groups, int group_size, double count, float eps, float* mean_rstd,
+                                  const float* gamma, const float* beta, const float* scale_shift, long ss_stride, float* coef,
                                   kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(sum_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && group_size % 8 == 0 && count > 0 && ns_a > 0,
              "kd_gn_finalize_oct: bad argument");
+  KD_REQUIRE(coef == nullptr || (gamma && beta), "kd_gn_finalize_oct: coefficients need gamma and beta");
   gn_finalize_oct_kernel<<<B, 32 * num_groups, 0, stream>>>(sum_a, n_oct_a, ns_a, scale_a, sum_b, sum_b ? n_oct_b : 0, sum_b ? ns_b : 0,
-                                                            scale_b, num_groups, group_size, count, eps, mean_rstd);
+                                                            scale_b, num_groups, group_size, count, eps, mean_rstd, gamma, beta,
+                                                            scale_shift, ss_stride, reinterpret_cast<float2*>(coef));
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import KdConvDesc, check
+from ._lib import KdConvDesc, KdConvFusion, check
 
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
 ACT_DTYPE = torch.float16  # 16-bit activation / weight dtype of the CUDA path (kd_common.cuh: h16), fp32 accumulation
@@ -135,6 +135,7 @@ def oct_stats(x):
 
 
 FUSED_STATS = True  # debugging switch: False forces the standalone statistics pass
+FUSED_PRE = True    # debugging switch: False keeps the separate GroupNorm-apply pass in front of the 3x3 convolutions
 
 
 def stats_of(x):
@@ -150,21 +151,43 @@ def stats_of(x):
 
 
 @_timed
-def gn_finalize_oct(stats_a, scale_a, stats_b, scale_b, group_size, num_groups, count, eps=1e-5):
+def gn_finalize_oct(stats_a, scale_a, stats_b, scale_b, group_size, num_groups, count, eps=1e-5, *, gamma=None, beta=None,
+                    scale_shift=None, want_coef=False):
+    """mean / rstd per (b, group); with want_coef also the per-channel affine [B, C, 2] = {A, B} of GroupNorm (+ time
+    scale/shift) on the raw sources (input of conv_gemm(pre_coef=...)).  Returns mean_rstd or (mean_rstd, coef)."""
     sa = stats_a.reduced()
     sb = stats_b.reduced() if stats_b is not None else None
     B = stats_a.B
     mean_rstd = torch.empty((B, num_groups, 2), device=sa.device, dtype=torch.float32)
+    coef = None
+    ss_stride = 0
+    if want_coef:
+        C = 8 * (stats_a.n_oct + (0 if stats_b is None else stats_b.n_oct))
+        coef = torch.empty((B, C, 2), device=sa.device, dtype=torch.float32)
+        _chk(gamma, torch.float32, "gamma")
+        _chk(beta, torch.float32, "beta")
+        if scale_shift is not None:
+            assert scale_shift.dtype == torch.float32 and scale_shift.stride(1) == 1 and scale_shift.shape[1] == 2 * C
+            ss_stride = scale_shift.stride(0)
     check(lib().kd_gn_finalize_oct(_ptr(sa), stats_a.n_oct, stats_a.ns, scale_a, _ptr(sb), 0 if stats_b is None else stats_b.n_oct,
                                    0 if stats_b is None else stats_b.ns, scale_b, B, num_groups, group_size, float(count), eps,
-                                   _ptr(mean_rstd), _stream()), "kd_gn_finalize_oct")
+                                   _ptr(mean_rstd), _ptr(gamma) if want_coef else None, _ptr(beta) if want_coef else None,
+                                   _ptr(scale_shift) if want_coef else None, ss_stride, _ptr(coef), _stream()), "kd_gn_finalize_oct")
     _count()
-    return mean_rstd
+    return (mean_rstd, coef) if want_coef else mean_rstd
+
+
+def conv_pre_supported(B, H, W, Ca, Cb, Cout, ksize=3):
+    """True when kd_conv_gemm_fused can apply the GroupNorm affine + SiLU to its input itself (3x3 halo kernel)."""
+    d = KdConvDesc(0, B, H, W, Ca, Cb, Cout, ksize, ACT_NONE, 0, 0, 0)
+    lay = (ctypes.c_int * 4)()
+    check(lib().kd_conv_stats_layout(ctypes.byref(d), lay), "kd_conv_stats_layout")
+    return FUSED_PRE and lay[3] == 1
 
 
 @_timed
 def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=ACT_NONE, out_mode=0, out_f32=False,
-              addend=None, addend_scale=None, out=None, want_stats=False, logit_w=None):
+              addend=None, addend_scale=None, out=None, want_stats=False, logit_w=None, pre_coef=None):
     """xa / xb: NHWC fp16 [B,H,W,C]; w: packed fp16 [Cout, taps*(Ca+Cb)]; returns NHWC (fp16 or fp32).
     want_stats / logit_w: ask the epilogue for fused GroupNorm statistics / GlobalContext logits of the output; they are
     attached to the result as `_kd_stats` / `_kd_logits` when this shape's kernel can emit them (else the consumer runs
@@ -197,7 +220,7 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
     stats = None
     lay = None
     if (want_stats or logit_w is not None) and FUSED_STATS:
-        lay = (ctypes.c_int * 3)()
+        lay = (ctypes.c_int * 4)()
         check(lib().kd_conv_stats_layout(ctypes.byref(d), lay), "kd_conv_stats_layout")
         if lay[0] > 0 and want_stats:
             stats = OctStats(torch.empty((lay[0], Cout // 8, 2), device=xa.device, dtype=torch.float32), 4, lay[1], lay[2], B, Cout // 8)
@@ -206,9 +229,13 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
         _chk(logit_w, torch.float32, "logit_w")
         logit_parts = torch.empty((Cout // 64, B, H * W), device=xa.device, dtype=torch.float32)
     with _ConvTimer(2.0 * B * H * W * Cout * taps * (Ca + Cb), (mode, B, H, W, Ca + Cb, Cout, ksize if mode == 0 else 2)):
+        if pre_coef is not None:
+            _chk(pre_coef, torch.float32, "pre_coef")
+            assert pre_coef.shape == (B, Ca + Cb, 2)
+        fz = KdConvFusion(None if stats is None else _ptr(stats.partial), None if logit_parts is None else _ptr(logit_w),
+                          _ptr(logit_parts), _ptr(pre_coef))
         check(lib().kd_conv_gemm_fused(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
-                                       _ptr(out), None if stats is None else _ptr(stats.partial),
-                                       None if logit_parts is None else _ptr(logit_w), _ptr(logit_parts), _stream()), "kd_conv_gemm")
+                                       _ptr(out), ctypes.byref(fz), _stream()), "kd_conv_gemm")
     if logit_parts is not None:
         out._kd_logits = logit_parts
     _count()

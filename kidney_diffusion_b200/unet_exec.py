@@ -342,17 +342,35 @@ class UnetExecutor:
         o = ops.conv_gemm(o.view(B, H, W, -1), P["wo"], None, ksize=1)
         return ops.layernorm_h16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
 
+    def _gn_coef(self, xa, xb, b_scale, G, gamma, beta, ss):
+        """Per-channel affine {A, B} of GroupNorm(+scale/shift) over the (virtual) concat [xa | b_scale * xb], for the
+        convolution's fused pre-activation (the activated tensor is never materialised)."""
+        B, H, W, Ca = xa.shape
+        C = Ca + (xb.shape[3] if exists(xb) else 0)
+        gs = C // G
+        _, coef = ops.gn_finalize_oct(ops.stats_of(xa), 1.0, ops.stats_of(xb) if exists(xb) else None, b_scale, gs, G,
+                                      count=gs * H * W, gamma=gamma, beta=beta, scale_shift=ss, want_coef=True)
+        return coef
+
+    def _norm_conv(self, xa, xb, b_scale, G, gamma, beta, ss, w, bias, **kw):
+        """Block.forward: conv3x3(SiLU(GroupNorm(x) * (scale + 1) + shift)); the norm is applied inside the conv kernel when
+        the shape runs on the halo kernel, else by a separate gn_apply pass."""
+        B, H, W, Ca = xa.shape
+        Cb = xb.shape[3] if exists(xb) else 0
+        if ops.conv_pre_supported(B, H, W, Ca, Cb, w.shape[0]):
+            coef = self._gn_coef(xa, xb, b_scale, G, gamma, beta, ss)
+            return ops.conv_gemm(xa, w, bias, xb=xb, ksize=3, pre_coef=coef, **kw)
+        ya, yb = self._gn(xa, xb, b_scale, G, gamma, beta, ss)
+        return ops.conv_gemm(ya, w, bias, xb=yb, ksize=3, **kw)
+
     def _resnet(self, P, xa, xb, ss_all, c):
-        B = xa.shape[0]
-        a1, a1b = self._gn(xa, xb, P.b_scale, P.G, P.g1, P.be1, None)
-        h = ops.conv_gemm(a1, P.w1, P.b1, xb=a1b, ksize=3, want_stats=not exists(P.xattn))
+        h = self._norm_conv(xa, xb, P.b_scale, P.G, P.g1, P.be1, None, P.w1, P.b1, want_stats=not exists(P.xattn))
         if exists(P.xattn):
             h = self._cross_attn(P.xattn, h, c)
         ss = ss_all[:, P.ss_off:P.ss_off + 2 * P.dim_out] if P.ss_off is not None else None
-        a2, _ = self._gn(h, None, 1.0, P.G, P.g2, P.be2, ss)
         if exists(P.gca):
             g = P.gca
-            h2 = ops.conv_gemm(a2, P.w2, P.b2, ksize=3, logit_w=g["wk"])
+            h2 = self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, logit_w=g["wk"])
             logits = getattr(h2, "_kd_logits", None)  # to_k from the conv epilogue (its bias cancels in the softmax)
             if logits is None:
                 logits = ops.rowdot(h2, g["wk"], g["bk"])
@@ -364,8 +382,8 @@ class UnetExecutor:
             return ops.gate_residual(h2, gate, xa, want_stats=True)
         if exists(P.wr):
             r = ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1)
-            return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=r, want_stats=True)
-        return ops.conv_gemm(a2, P.w2, P.b2, ksize=3, addend=xa, want_stats=True)
+            return self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, addend=r, want_stats=True)
+        return self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, addend=xa, want_stats=True)
 
     def _transformer(self, P, x, c):
         B, H, W, C = x.shape

@@ -78,3 +78,16 @@ if want("c3_256"):
     px = B * S * S
     ms = timeit(lambda: ops.conv_gemm(xa, w, bias, ksize=3, want_stats=True))
     report("3x3 256->256 @256 +stats", ms, 2.0 * px * 9 * 256 * 256, px * 2 * 512)
+if want("pre"):
+    for (S, Cin, Cout) in ((256, 256, 256), (1024, 128, 128)):
+        xa = act(B, S, S, Cin)
+        w = act(Cout, 9 * Cin)
+        bias = torch.randn(Cout, device=dev)
+        px = B * S * S
+        st = ops.oct_stats(xa)
+        gamma, beta = torch.randn(Cin, device=dev), torch.randn(Cin, device=dev)
+        _, coef = ops.gn_finalize_oct(st, 1.0, None, 1.0, Cin // 8, 8, count=(Cin // 8) * S * S, gamma=gamma, beta=beta, want_coef=True)
+        ms = timeit(lambda: ops.conv_gemm(xa, w, bias, ksize=3, want_stats=True, pre_coef=coef))
+        report(f"3x3 {Cin}->{Cout} @{S} +stats, fused GroupNorm+SiLU input", ms, 2.0 * px * 9 * Cin * Cout, px * 2 * (Cin + Cout))
+        ms = timeit(lambda: ops.conv_gemm(xa, w, bias, ksize=3, want_stats=True))
+        report(f"3x3 {Cin}->{Cout} @{S} +stats, plain input", ms, 2.0 * px * 9 * Cin * Cout, px * 2 * (Cin + Cout))

@@ -615,3 +615,58 @@ def test_fused_global_context_logits_match_rowdot(cuda_lib, B, H, W, Cin, Cout, 
     assert float((alone.double().cpu() - exact).abs().max()) < 1e-5 * scale + 1e-5
     pa, pb = ops.gca_pool(out, parts), ops.gca_pool(out, alone)
     assert torch.allclose(pa, pb, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,W,Ca,Cb,Cout,use_ss,use_add", [
+    (2, 32, 32, 128, 0, 128, True, False),
+    (1, 40, 24, 64, 64, 256, False, True),     # two sources (skip concat with scale), partial tiles, TMA-fed addend
+    (3, 16, 8, 128, 0, 192, True, True),       # single tile per image, Cout not a multiple of 128, odd tile count (idle pair half)
+    (1, 128, 64, 256, 0, 128, False, False),
+])
+def test_conv_fused_groupnorm_preactivation(cuda_lib, B, H, W, Ca, Cb, Cout, use_ss, use_add):
+    """conv3x3 with the GroupNorm affine + SiLU applied to the halo tile in shared memory (pre_coef) == the separate
+    gn_apply pass followed by the same convolution."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(H * 3 + Cout + Ca)
+    C, G = Ca + Cb, 8
+    gs = C // G
+    b_scale = 2 ** -0.5
+    xa = nhwc(torch.randn(B, Ca, H, W, generator=g) * 2 + 0.3)
+    xb = nhwc(torch.randn(B, Cb, H, W, generator=g)) if Cb else None
+    w = bf(torch.randn(Cout, 9 * C, generator=g) / math.sqrt(9 * C)).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    ss = (torch.randn(B, 2 * C + 5, generator=g) * 0.3).to(DEV)[:, 3:3 + 2 * C] if use_ss else None  # strided column slice
+    add = nhwc(torch.randn(B, Cout, H, W, generator=g)) if use_add else None
+    assert ops.conv_pre_supported(B, H, W, Ca, Cb, Cout)
+    sa, sb = ops.oct_stats(xa), (ops.oct_stats(xb) if Cb else None)
+    mr, coef = ops.gn_finalize_oct(sa, 1.0, sb, b_scale, gs, G, count=gs * H * W, gamma=gamma, beta=beta, scale_shift=ss, want_coef=True)
+    kw = dict(group_size=gs, num_groups=G, scale_shift=ss, ctot=C)
+    ya = ops.gn_apply(xa, mr, gamma, beta, c_offset=0, **kw)
+    yb = ops.gn_apply(xb, mr, gamma, beta, c_offset=Ca, src_scale=b_scale, **kw) if Cb else None
+    ref = ops.conv_gemm(ya, w, bias, xb=yb, ksize=3, addend=add, want_stats=True)
+    got = ops.conv_gemm(xa, w, bias, xb=xb, ksize=3, addend=add, want_stats=True, pre_coef=coef)
+    err = rel_l2(got, ref)
+    print(f"fused pre-activation vs separate pass rel-L2 {err:.2e}")
+    assert torch.isfinite(got.float()).all()
+    assert err < 1e-3
+    # against plain PyTorch: GroupNorm over the virtual concat -> (scale + 1, shift) -> SiLU -> conv
+    xcat = xa.float().cpu().permute(0, 3, 1, 2)
+    if Cb:
+        xcat = torch.cat((xcat, xb.float().cpu().permute(0, 3, 1, 2) * b_scale), 1)
+    y = F.group_norm(xcat, G, gamma.cpu(), beta.cpu(), eps=1e-5)
+    if use_ss:
+        sc, sh = ss.cpu()[:, :C], ss.cpu()[:, C:]
+        y = y * (sc[:, :, None, None] + 1) + sh[:, :, None, None]
+    y = F.silu(y)
+    wt = w.float().cpu().view(Cout, 3, 3, C).permute(0, 3, 1, 2)
+    o = F.conv2d(y, wt, bias.cpu(), padding=1)
+    if use_add:
+        o = o + add.float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(from_nhwc(got), o) < 4e-3
+    # the fused statistics of the output are those of the stored tensor
+    st = got._kd_stats.reduced().double().cpu().sum(1)
+    ov = got.double().cpu().view(B, H * W, Cout // 8, 8)
+    exact = torch.stack((ov.sum(dim=(1, 3)), (ov * ov).sum(dim=(1, 3))), dim=-1)
+    assert float(((st - exact).abs() / (exact.abs() + 1.0)).max()) < 2e-5
