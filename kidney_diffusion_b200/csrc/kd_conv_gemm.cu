@@ -372,6 +372,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
   }
 }
 
+// accumulator stages in TMEM (512 columns): BN = 256 -> 2, BN = 128 -> 4 (the MMA can run up to three tiles ahead of the
+// epilogue, which at BN = 128 takes about as long per tile as the MMAs and otherwise alternates with them)
+template <int BN>
+struct AccStages {
+  static constexpr uint32_t N = 512 / BN;
+};
+
 // ---- epilogue role of the CTA-pair kernels (warps 4..11): drains the double-buffered TMEM accumulator tile by tile.
 // Two sets of 4 warps (one warp of each set per SM sub-partition): set 0 takes the even 64-column groups of a tile, set 1 the
 // odd ones; an "item" is one such group: 128 rows x 64 columns, staged in a 16 KB 128B-swizzled smem tile and written with
@@ -389,6 +396,7 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
                                                    uint64_t* tmem_empty_bar, const uint32_t epi_smem, float* epi_aux, const int warp,
                                                    const int lane, const uint32_t rank, const int cluster_id, const int num_clusters,
                                                    const int num_pair_tiles) {
+  constexpr uint32_t ACC = AccStages<BN>::N;
   const CUtensorMap& map_out = *map_out_ptr;
   const int quarter = warp & 3;
   const int set = (warp - 4) >> 2;
@@ -427,7 +435,7 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
   int aux_key = -1;
   uint32_t tile_iter = 0;
   for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
-    const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+    const uint32_t as = tile_iter % ACC, aph = (tile_iter / ACC) & 1;
     const int n_tile = t % p.n_tiles;
     int m_tile = (t / p.n_tiles) * 2 + (int)rank;
     const int tile_w = m_tile % p.tiles_w;
@@ -631,7 +639,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   constexpr int EPI_BUFS = TADD ? 4 : 2;  // 16 KB staging tiles: one per epilogue set, two with the TMA-fed addend
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  constexpr uint32_t ACC = AccStages<BN>::N;
+  constexpr uint32_t TMEM_COLS = 512;  // ACC accumulator stages
   // instruction descriptor: D fp32, A = B = h16, K-major, N = BN, M = 256 (pair)
   constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
@@ -645,8 +654,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -669,7 +678,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < (int)ACC; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), 16);  // 8 epilogue warps x 2 CTAs
     }
@@ -730,7 +739,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (rank == 0) {
       uint32_t it = 0, tile_iter = 0;
       for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
-        const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+        const uint32_t as = tile_iter % ACC, aph = (tile_iter / ACC) & 1;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -794,7 +803,8 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                       const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
                       const __grid_constant__ CUtensorMap map_add, const ConvParams p, const int num_pair_tiles) {
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t ACC = AccStages<BN>::N;
+  constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
@@ -814,9 +824,9 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* b_full = a_empty + AS;
   uint64_t* b_empty = b_full + BS;
   uint64_t* tmem_full_bar = b_empty + BS;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  static_assert((2 * AS + 2 * BS + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
+  static_assert((2 * AS + 2 * BS + 2 * ACC) * 8 + 4 <= 320, "barrier block overflows its 320 bytes");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -846,7 +856,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(smem_u32(&b_empty[s]), 1);
     }
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < (int)ACC; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), 16);
     }
@@ -920,7 +930,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (rank == 0) {
       uint32_t ita = 0, itb = 0, tile_iter = 0;
       for (int t = cluster_id; t < num_pair_tiles; t += num_clusters, ++tile_iter) {
-        const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+        const uint32_t as = tile_iter % ACC, aph = (tile_iter / ACC) & 1;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;

@@ -306,13 +306,10 @@ def sinu_emb(t, weights):
 
 # ------------------------------------------------------------------------------------------------ GroupNorm
 def _nblk(HW, C, B):
-    oct_ = C // 8
-    threads = 256 if oct_ >= 256 else (256 // oct_) * oct_
-    lanes = max(1, threads // oct_)
-    # independent of the batch size on purpose: a sample's reduction order (hence its bits) must not depend on which
-    # other patches share its batch (patch-grid invariance across GPU counts)
-    want = 148 * 4
-    return int(max(1, min(want, -(-HW // lanes))))
+    # blocks per image of the pixel-chunked reduction kernels; independent of the batch size on purpose: a sample's
+    # reduction order (hence its bits) must not depend on which other patches share its batch (patch-grid invariance
+    # across GPU counts)
+    return int(lib().kd_elementwise_blocks(HW, C))
 
 
 @_timed

@@ -42,3 +42,19 @@ fb = torch.randn(3, device=dev)
 ms = timeit(lambda: ops.final_conv(add, x, w, fb))
 gb = (add.numel() * 2 + 2 * x.numel() * 4) / 1e9
 print(f"final_conv B={B}: {ms:.3f} ms  ({gb / ms * 1e3:.0f} GB/s algorithmic)")
+
+# GlobalContext pooling: kd_gca_pool + kd_gca_finalize per level of the SR UNet
+import ctypes
+from kidney_diffusion_b200.ops import _ptr, _stream, lib
+for (S2, C) in ((512, 128), (256, 256), (128, 512), (64, 1024)):
+    xg = torch.randn(B, S2, S2, C, device=dev).half()
+    lg = torch.randn(max(1, C // 64), B, S2 * S2, device=dev)
+    HW = S2 * S2
+    nblk = lib().kd_elementwise_blocks(HW, C)
+    part = torch.empty((B, nblk, C), device=dev)
+    ml = torch.empty((B, nblk, 2), device=dev)
+    pooled = torch.empty((B, C), device=dev)
+    t_pool = timeit(lambda: lib().kd_gca_pool(_ptr(xg), _ptr(lg), lg.shape[0], B, HW, C, nblk, _ptr(part), _ptr(ml), _stream()), 10)
+    t_fin = timeit(lambda: lib().kd_gca_finalize(_ptr(part), _ptr(ml), B, nblk, C, _ptr(pooled), _stream()), 10)
+    gb = xg.numel() * 2 / 1e9
+    print(f"gca_pool {S2}^2 x {C}: pool {t_pool * 1e3:7.1f} us ({gb / t_pool * 1e3:5.0f} GB/s, nblk {nblk}), finalize {t_fin * 1e3:6.1f} us")
