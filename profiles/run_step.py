@@ -11,7 +11,8 @@ from kidney_diffusion_b200.factories import init_imagen_ultra_res, randomize_zer
 from kidney_diffusion_b200.imagen import CounterNoise
 
 B = int(os.environ.get("KD_PROFILE_BATCH", "1"))
-S = int(os.environ.get("KD_PROFILE_SIZE", "1024"))
+U = int(os.environ.get("KD_PROFILE_UNET", "3"))   # cascade stage: 1 (64^2 base), 2 (256^2), 3 (1024^2)
+S = int(os.environ.get("KD_PROFILE_SIZE", str({1: 64, 2: 256, 3: 1024}[U])))
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 imagen = init_imagen_ultra_res(1, 3, version="v_param")
@@ -22,7 +23,8 @@ noise = CounterNoise(1234, 0)
 g = torch.Generator().manual_seed(1)
 cond = torch.rand(B, 3, S, S, generator=g).to(dev)
 lowres = torch.randn(B, 3, S, S, generator=g).to(dev)
-run = imagen.stage_run(3, (B, 3, S, S), noise=noise, lowres_cond_img=lowres, lowres_noise_level=0.2, cond_images=cond)
+run = imagen.stage_run(U, (B, 3, S, S), noise=noise, lowres_cond_img=lowres if U > 1 else None,
+                       lowres_noise_level=0.2 if U > 1 else None, cond_images=cond)
 run.step(0)
 run.step(1)
 torch.cuda.synchronize()
