@@ -216,8 +216,20 @@ def run_b200(args):
     conv_flops = sum(p[0] for p in prof)
     conv_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
     achieved = conv_flops / (conv_ms / 1e3) / 1e12
+    # DRAM bytes of the dominant launch shape from the committed `ncu --set full` capture (profiles/r01_traffic.json), scaled
+    # from the captured batch to this run's: the kernel moves its algorithmic bytes once (no re-reads)
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * B / tj["batch"]
+        traffic_note = (f"{tj['kernel']} on {tj['shape']}: ncu dram read+write {tj['dram_bytes_read'] + tj['dram_bytes_write']:.3e} B at B={tj['batch']} "
+                        f"(algorithmic {tj['algorithmic_bytes']:.3e} B), scaled to B={B}; source {tj['source']}")
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=achieved / peaks["tf_sustained"],
-                    traffic=None, kernel="conv_gemm_kernel (tcgen05 implicit GEMM)", launches_per_step=len(prof),
+                    traffic=traffic, traffic_note=traffic_note,
+                    kernel="conv_gemm_halo_kernel / conv_gemm_pair_kernel / init_conv_kernel (tcgen05 implicit GEMM, cta_group::2, TMEM)",
+                    launches_per_step=len(prof),
                     conv_ms_per_step=conv_ms, conv_share_of_step=conv_ms / ms_per_step, peak_source=peaks["source"] + " sustained bf16",
                     how="sum of algorithmic conv/linear FLOPs of one step / sum of per-launch CUDA-event durations (eager replay of a timed step)")
     unet_tflops = B * UNET3_GFLOP_PER_SAMPLE_1024 * (S / 1024) ** 2 / 1e3 / (ms_per_step / 1e3)

@@ -15,7 +15,7 @@ U = int(os.environ.get("KD_PROFILE_UNET", "3"))   # cascade stage: 1 (64^2 base)
 S = int(os.environ.get("KD_PROFILE_SIZE", str({1: 64, 2: 256, 3: 1024}[U])))
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-imagen = init_imagen_ultra_res(1, 3, version="v_param")
+imagen = init_imagen_ultra_res(1, U, version="v_param")
 randomize_zero_init_(imagen)
 imagen = imagen.to(dev).eval()
 imagen.use_cuda_graph = False
