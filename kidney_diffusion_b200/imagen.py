@@ -68,7 +68,7 @@ class CounterNoise:
 class _StepGraph:
     """One UNet forward for fixed (B, S) captured as a CUDA graph (~800 kernel launches per step otherwise)."""
 
-    def __init__(self, ex, B, S, channels, lowres_t, device, drop=0.0):
+    def __init__(self, ex, B, S, channels, lowres_t, device, drop=0.0, pool=None):
         self.drop = drop
         self.x = torch.zeros((B, channels, S, S), device=device, dtype=torch.float32)
         self.time = torch.zeros((B,), device=device, dtype=torch.float32)
@@ -82,7 +82,10 @@ class _StepGraph:
         torch.cuda.current_stream(device).wait_stream(stream)
         before = ops.launch_count
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # all step graphs of one conditioning kind share a memory pool: they are replayed one at a time and `pred` is consumed
+        # (dynamic threshold + update) before the next replay, so the pool is as large as the biggest graph, not their sum --
+        # the patch-grid sampler meets every batch size 1..16 per stage
+        with torch.cuda.graph(self.graph, pool=pool):
             self.pred = ex.forward(self.x, self.time, self.lowres_t, drop=drop)
         self.launches = ops.launch_count - before
 
@@ -218,6 +221,7 @@ class Imagen(nn.Module):
         self.noise_fn = None  # tests inject (site, shape, **key) -> tensor; default CounterNoise
         self.noise_seed = 0
         self._graphs = {}
+        self._pools = {}
         self.step_hook = None  # optional callable(dict) per inner iteration (parity taps)
 
     @property
@@ -247,9 +251,14 @@ class Imagen(nn.Module):
         key = (id(ex), B, S, exists(ex.init_base), exists(ex.lowres_img), float(drop) if has_text else None)
         g = self._graphs.get(key)
         if g is None:
-            if len(self._graphs) > 8:
+            if len(self._graphs) > 96:
                 self._graphs.clear()
-            g = self._graphs[key] = _StepGraph(ex, B, S, self.channels, lowres_t, img.device, drop=drop)
+            # conditional and null-conditioning graphs (classifier-free guidance) keep separate pools: both predictions are
+            # alive when they are mixed
+            pkey = (str(img.device), float(drop))
+            if pkey not in self._pools:
+                self._pools[pkey] = torch.cuda.graph_pool_handle()
+            g = self._graphs[key] = _StepGraph(ex, B, S, self.channels, lowres_t, img.device, drop=drop, pool=self._pools[pkey])
         return g(img, time_row, lowres_t)
 
     def stage_run(self, unet_number, shape, *, noise, lowres_cond_img=None, lowres_noise_level=None, text_embeds=None, text_mask=None,

@@ -12,6 +12,8 @@ from kidney_diffusion_b200.build import build_library
 build_library()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cases = sys.argv[2:] or ["all"]
+if os.environ.get("KD_CONV_IMPL"):
+    ops.set_conv_impl(int(os.environ["KD_CONV_IMPL"]))
 dev = "cuda"
 
 
@@ -89,5 +91,8 @@ if want("pre"):
         _, coef = ops.gn_finalize_oct(st, 1.0, None, 1.0, Cin // 8, 8, count=(Cin // 8) * S * S, gamma=gamma, beta=beta, want_coef=True)
         ms = timeit(lambda: ops.conv_gemm(xa, w, bias, ksize=3, want_stats=True, pre_coef=coef))
         report(f"3x3 {Cin}->{Cout} @{S} +stats, fused GroupNorm+SiLU input", ms, 2.0 * px * 9 * Cin * Cout, px * 2 * (Cin + Cout))
+        add = act(B, S, S, Cout)
+        ms = timeit(lambda: ops.conv_gemm(xa, w, bias, ksize=3, want_stats=True, pre_coef=coef, addend=add))
+        report(f"3x3 {Cin}->{Cout} @{S} +stats, fused GN input + residual", ms, 2.0 * px * 9 * Cin * Cout, px * 2 * (Cin + 2 * Cout))
         ms = timeit(lambda: ops.conv_gemm(xa, w, bias, ksize=3, want_stats=True))
         report(f"3x3 {Cin}->{Cout} @{S} +stats, plain input", ms, 2.0 * px * 9 * Cin * Cout, px * 2 * (Cin + Cout))
