@@ -12,6 +12,12 @@ void kd_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_kd_pdl = 1;
+extern "C" int kd_exp_set_pdl(int on) {
+  g_kd_pdl = on;
+  return 0;
+}
+
 int kd_num_sms() {
   static int sms = 0;
   if (sms == 0) {

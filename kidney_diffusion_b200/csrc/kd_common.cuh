@@ -37,6 +37,27 @@ void kd_set_error(const char* fmt, ...);
   } while (0)
 
 static inline int kd_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch: the kernel may be scheduled while its stream predecessor is still draining; it must execute
+// kd_pdl_wait() before touching global memory (which waits for the predecessor's completion and memory flush).  In a step of
+// ~550-730 small launches the per-launch scheduling gap is what this hides (CUDA graphs keep these edges programmatic).
+#ifdef __CUDACC__
+extern int g_kd_pdl;  // kd_abi.cu; 0 disables (test hook)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t kd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_kd_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 int kd_num_sms();
 
 // ---------------------------------------------------------------- device helpers
@@ -52,6 +73,9 @@ typedef __half2 h162;
 struct __align__(16) h16x8 {
   h162 v[4];
 };
+
+__device__ __forceinline__ void kd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void kd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float sat16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
 

@@ -98,6 +98,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  kd_pdl_wait();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  kd_pdl_trigger();
 
   if (warp == 0) {
     // ================================================================ TMA producer (one elected lane)
@@ -690,6 +692,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  kd_pdl_wait();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  kd_pdl_trigger();
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs, one lane each)
@@ -868,6 +872,8 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  kd_pdl_wait();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  kd_pdl_trigger();
 
   if (warp == 0) {
     // ================================================================ weight (B) TMA producer (both CTAs, one lane each)
@@ -1153,8 +1159,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, 
       configured = true;
     }
   }
-  conv_gemm_kernel<BN, STAGES><<<(unsigned)grid, NUM_THREADS, SMEM, stream>>>(ma, mb, mw, p);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(conv_gemm_kernel<BN, STAGES>, dim3((unsigned)grid), dim3(NUM_THREADS), SMEM, stream, ma, mb, mw, p));
   return KD_OK;
 }
 
@@ -1205,8 +1210,8 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
   int clusters = kd_num_sms() / 2;
   if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_pair_kernel<BN, STAGES, TADD><<<2 * clusters, NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(conv_gemm_pair_kernel<BN, STAGES, TADD>, dim3(2 * clusters), dim3(NUM_THREADS2), SMEM, stream, ma, mb, mw, mo, madd, p,
+                    (int)pair_tiles));
   return KD_OK;
 }
 
@@ -1237,8 +1242,8 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   KD_REQUIRE(pair_tiles < 2147483647LL, "kd_conv_gemm: too many tiles");
   int clusters = kd_num_sms() / 2;
   if (pair_tiles < clusters) clusters = (int)pair_tiles;
-  conv_gemm_halo_kernel<BN, AS, BS, TADD, TPS, PRE><<<2 * clusters, PRE ? NUM_THREADS3 : NUM_THREADS2, SMEM, stream>>>(ma, mb, mw, mo, madd, p, (int)pair_tiles);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(conv_gemm_halo_kernel<BN, AS, BS, TADD, TPS, PRE>, dim3(2 * clusters), dim3(PRE ? NUM_THREADS3 : NUM_THREADS2), SMEM, stream,
+                    ma, mb, mw, mo, madd, p, (int)pair_tiles));
   return KD_OK;
 }
 

@@ -350,6 +350,8 @@ __global__ void gca_finalize_kernel(const float* __restrict__ part, const float*
 __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __restrict__ gate, const h16* __restrict__ res,
                                      h16* __restrict__ out, float* __restrict__ oct_partial, long HW, int C, int nblk) {
   extern __shared__ float sm[];  // [T][2] when statistics are requested
+  kd_pdl_wait();
+  kd_pdl_trigger();
   const int oct = C >> 3;
   const int lanes = blockDim.x / oct;
   const int o = threadIdx.x % oct;
@@ -720,9 +722,9 @@ extern "C" int kd_gate_residual(const void* h, const float* gate, const void* re
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
   const int nblk = kd_elementwise_blocks(HW, C);
-  gate_residual_kernel<<<dim3(nblk, B), T, oct_partial ? T * 2 * sizeof(float) : 0, stream>>>(
-      reinterpret_cast<const h16*>(h), gate, reinterpret_cast<const h16*>(res), reinterpret_cast<h16*>(out), oct_partial, HW, C, nblk);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(gate_residual_kernel, dim3(nblk, B), dim3(T), oct_partial ? T * 2 * sizeof(float) : 0, stream,
+                    reinterpret_cast<const h16*>(h), gate, reinterpret_cast<const h16*>(res), reinterpret_cast<h16*>(out), oct_partial, HW, C,
+                    nblk));
   return KD_OK;
 }
 
