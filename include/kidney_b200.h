@@ -147,6 +147,14 @@ int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, float scale_a,
                        const float* gamma /* [C] */, const float* beta, const float* scale_shift /* [B][ss_stride]: scale | shift, or NULL */,
                        long ss_stride, float* coef /* [B][C][2] or NULL */, kd_stream_t stream);
 
+/* kd_oct_reduce + kd_gn_finalize_oct in ONE launch (bit-identical results): the last block to finish an image finalizes it.
+ * scratch: B * (NS_a * n_oct_a + NS_b * n_oct_b) * 2 floats (NS = kd_oct_reduce_splits of each source); counter: >= B
+ * unsigned ints, zero before the first call (the kernel leaves them zero). */
+int kd_gn_reduce_finalize(const float* partial_a, int rpt_a, int tiles_a, int TB_a, int n_oct_a, float scale_a, const float* partial_b,
+                          int rpt_b, int tiles_b, int TB_b, int n_oct_b, float scale_b, int B, int num_groups, int group_size,
+                          double count, float eps, float* scratch, unsigned int* counter, float* mean_rstd, const float* gamma,
+                          const float* beta, const float* scale_shift, long ss_stride, float* coef, kd_stream_t stream);
+
 /* ------------------------------------------------------------------ K4: GlobalContext gate
  * replaces: GlobalContext.forward (to_k 1x1 conv -> softmax over H*W -> weighted channel sum) and h * gate + residual. */
 int kd_rowdot(const void* x /* fp16 [B,HW,C] */, const float* w /* [C] */, const float* bias /* [1] or NULL */, float* out /* [B,HW] */,

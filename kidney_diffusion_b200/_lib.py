@@ -47,6 +47,7 @@ SIGNATURES = {
     "kd_gn_stats": (c_int, [_P, _I, _L, _I, _I, _I, _I, _P, _I, _P]),
     "kd_gn_finalize": (c_int, [_P, _I, _F, _P, _I, _F, _I, _I, c_double, _F, _P, _P]),
     "kd_gn_apply": (c_int, [_P, _P, _I, _L, _I, _I, _I, _I, _F, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "kd_gn_reduce_finalize": (c_int, [_P, _I, _I, _I, _I, _F, _P, _I, _I, _I, _I, _F, _I, _I, _I, c_double, _F, _P, _P, _P, _P, _P, _P, _L, _P, _P]),
     "kd_rowdot": (c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
     "kd_gca_pool": (c_int, [_P, _P, _I, _I, _L, _I, _I, _P, _P, _P]),
     "kd_gca_finalize": (c_int, [_P, _P, _I, _I, _I, _P, _P]),

@@ -550,6 +550,117 @@ __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int
   }
 }
 
+// ---- one launch for "reduce the producer's octet partials + finalize": grid (NS_a + NS_b, B) blocks of 256 threads do the
+// first-level sums of the two sources; the last block to finish for an image (self-resetting arrival counter) runs the
+// finalize.  Same arithmetic, in the same order, as kd_oct_reduce followed by kd_gn_finalize_oct (bit-identical), one launch
+// instead of two or three per GroupNorm (104 GroupNorms per 1024^2 step).
+struct OctSrc {
+  const float* partial;
+  int rpt, tiles, TB, n_oct, NS;
+  float* out;  // [B][NS][n_oct][2]
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) gn_reduce_finalize_kernel(const OctSrc a, const OctSrc b2, int G, int group_size, double count,
+                                                                 float eps, float* __restrict__ mean_rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ scale_shift, long ss_stride,
+                                                                 float2* __restrict__ coef, unsigned int* __restrict__ counter) {
+  __shared__ double sred[256 * 2];
+  __shared__ bool s_last;
+  const int b = blockIdx.y;
+  {
+    const bool first = (int)blockIdx.x < a.NS;
+    const OctSrc& s = first ? a : b2;
+    const int sp = first ? (int)blockIdx.x : (int)blockIdx.x - a.NS;
+    const int n_oct = s.n_oct, lanes = 256 / n_oct;
+    const int o = threadIdx.x % n_oct, l = threadIdx.x / n_oct;
+    const int tile_b = b / s.TB, sub = b % s.TB, rpb = s.rpt / s.TB;
+    const long cnt = (long)s.tiles * rpb;
+    const long per = (cnt + s.NS - 1) / s.NS;
+    const long r0 = (long)sp * per, r1 = (r0 + per < cnt) ? r0 + per : cnt;
+    double s1 = 0.0, s2 = 0.0;
+    if (l < lanes) {
+      const float2* pp = reinterpret_cast<const float2*>(s.partial);
+      for (long i = r0 + l; i < r1; i += lanes) {
+        const long row = ((long)tile_b * s.tiles + i / rpb) * s.rpt + (long)sub * rpb + i % rpb;
+        const float2 v = pp[row * n_oct + o];
+        s1 += v.x;
+        s2 += v.y;
+      }
+    }
+    sred[threadIdx.x * 2] = s1;
+    sred[threadIdx.x * 2 + 1] = s2;
+    __syncthreads();
+    if ((int)threadIdx.x < n_oct) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int k = 0; k < lanes; ++k) {
+        a1 += sred[(k * n_oct + threadIdx.x) * 2];
+        a2 += sred[(k * n_oct + threadIdx.x) * 2 + 1];
+      }
+      reinterpret_cast<float2*>(s.out)[((long)b * s.NS + sp) * n_oct + threadIdx.x] = make_float2((float)a1, (float)a2);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = (unsigned int)(a.NS + b2.NS);
+    s_last = atomicAdd(&counter[b], 1u) == total - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31;
+  const int na = a.n_oct, nb = b2.NS > 0 ? b2.n_oct : 0;
+  for (int g = threadIdx.x >> 5; g < G; g += 8) {
+    double s = 0.0, ss = 0.0;
+    for (int o = lane; o < na + nb; o += 32) {
+      if ((o * 8) / group_size != g) continue;
+      if (o < na) {
+        for (int k = 0; k < a.NS; ++k) {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(a.out) + ((long)b * a.NS + k) * na + o);
+          s += (double)v.x * a.scale;
+          ss += (double)v.y * a.scale * a.scale;
+        }
+      } else {
+        for (int k = 0; k < b2.NS; ++k) {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(b2.out) + ((long)b * b2.NS + k) * nb + (o - na));
+          s += (double)v.x * b2.scale;
+          ss += (double)v.y * b2.scale * b2.scale;
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    const double mean_d = s / count;
+    double var = ss / count - mean_d * mean_d;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (lane == 0) {
+      mean_rstd[((long)b * G + g) * 2] = mean;
+      mean_rstd[((long)b * G + g) * 2 + 1] = rstd;
+    }
+    if (coef != nullptr) {
+      const int Ctot = (na + nb) * 8, Ca = na * 8;
+      for (int c = g * group_size + lane; c < (g + 1) * group_size; c += 32) {
+        const float ga = gamma[c], be = beta[c];
+        float aa = rstd * ga, cc = be - mean * rstd * ga;
+        if (scale_shift != nullptr) {
+          const float sc = scale_shift[(long)b * ss_stride + c] + 1.0f;
+          const float sh = scale_shift[(long)b * ss_stride + Ctot + c];
+          aa *= sc;
+          cc = cc * sc + sh;
+        }
+        coef[(long)b * Ctot + c] = make_float2(aa * (c < Ca ? a.scale : b2.scale), cc);
+      }
+    }
+  }
+  if (threadIdx.x == 0) counter[b] = 0;  // ready for the next launch (stream order)
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm (one warp per token)
 template <bool F32>
 __global__ void layernorm_kernel(const void* __restrict__ x_, const float* __restrict__ g, const float* __restrict__ bias,
@@ -769,6 +880,35 @@ extern "C" int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, flo
   gn_finalize_oct_kernel<<<B, 32 * num_groups, 0, stream>>>(sum_a, n_oct_a, ns_a, scale_a, sum_b, sum_b ? n_oct_b : 0, sum_b ? ns_b : 0,
                                                             scale_b, num_groups, group_size, count, eps, mean_rstd, gamma, beta,
                                                             scale_shift, ss_stride, reinterpret_cast<float2*>(coef));
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gn_reduce_finalize(const float* partial_a, int rpt_a, int tiles_a, int TB_a, int n_oct_a, float scale_a,
+                                     const float* partial_b, int rpt_b, int tiles_b, int TB_b, int n_oct_b, float scale_b, int B,
+                                     int num_groups, int group_size, double count, float eps, float* scratch, unsigned int* counter,
+                                     float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift, long ss_stride,
+                                     float* coef, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(partial_a && scratch && counter && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && group_size % 8 == 0 && count > 0,
+             "kd_gn_reduce_finalize: bad argument");
+  KD_REQUIRE(n_oct_a > 0 && n_oct_a <= 256 && rpt_a > 0 && tiles_a > 0 && TB_a > 0 && rpt_a % TB_a == 0, "kd_gn_reduce_finalize: bad source a");
+  KD_REQUIRE(!partial_b || (n_oct_b > 0 && n_oct_b <= 256 && rpt_b > 0 && tiles_b > 0 && TB_b > 0 && rpt_b % TB_b == 0),
+             "kd_gn_reduce_finalize: bad source b");
+  KD_REQUIRE(coef == nullptr || (gamma && beta), "kd_gn_reduce_finalize: coefficients need gamma and beta");
+  OctSrc a, b2;
+  a.partial = partial_a; a.rpt = rpt_a; a.tiles = tiles_a; a.TB = TB_a; a.n_oct = n_oct_a; a.scale = scale_a;
+  a.NS = kd_oct_reduce_splits(rpt_a, tiles_a, TB_a);
+  a.out = scratch;
+  b2 = a;
+  b2.NS = 0;
+  if (partial_b) {
+    b2.partial = partial_b; b2.rpt = rpt_b; b2.tiles = tiles_b; b2.TB = TB_b; b2.n_oct = n_oct_b; b2.scale = scale_b;
+    b2.NS = kd_oct_reduce_splits(rpt_b, tiles_b, TB_b);
+    b2.out = scratch + (size_t)B * a.NS * n_oct_a * 2;
+  }
+  gn_reduce_finalize_kernel<<<dim3(a.NS + b2.NS, B), 256, 0, stream>>>(a, b2, num_groups, group_size, count, eps, mean_rstd, gamma, beta,
+                                                                       scale_shift, ss_stride, reinterpret_cast<float2*>(coef), counter);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -135,6 +135,7 @@ def oct_stats(x):
 
 
 FUSED_STATS = True  # debugging switch: False forces the standalone statistics pass
+FUSED_REDUCE = True  # debugging switch: False runs kd_oct_reduce and kd_gn_finalize_oct as separate launches
 FUSED_PRE = True    # debugging switch: False keeps the separate GroupNorm-apply pass in front of the 3x3 convolutions
 
 
@@ -155,26 +156,51 @@ def gn_finalize_oct(stats_a, scale_a, stats_b, scale_b, group_size, num_groups, 
                     scale_shift=None, want_coef=False):
     """mean / rstd per (b, group); with want_coef also the per-channel affine [B, C, 2] = {A, B} of GroupNorm (+ time
     scale/shift) on the raw sources (input of conv_gemm(pre_coef=...)).  Returns mean_rstd or (mean_rstd, coef)."""
-    sa = stats_a.reduced()
-    sb = stats_b.reduced() if stats_b is not None else None
     B = stats_a.B
-    mean_rstd = torch.empty((B, num_groups, 2), device=sa.device, dtype=torch.float32)
+    dev = stats_a.partial.device
+    mean_rstd = torch.empty((B, num_groups, 2), device=dev, dtype=torch.float32)
     coef = None
     ss_stride = 0
     if want_coef:
         C = 8 * (stats_a.n_oct + (0 if stats_b is None else stats_b.n_oct))
-        coef = torch.empty((B, C, 2), device=sa.device, dtype=torch.float32)
+        coef = torch.empty((B, C, 2), device=dev, dtype=torch.float32)
         _chk(gamma, torch.float32, "gamma")
         _chk(beta, torch.float32, "beta")
         if scale_shift is not None:
             assert scale_shift.dtype == torch.float32 and scale_shift.stride(1) == 1 and scale_shift.shape[1] == 2 * C
             ss_stride = scale_shift.stride(0)
-    check(lib().kd_gn_finalize_oct(_ptr(sa), stats_a.n_oct, stats_a.ns, scale_a, _ptr(sb), 0 if stats_b is None else stats_b.n_oct,
-                                   0 if stats_b is None else stats_b.ns, scale_b, B, num_groups, group_size, float(count), eps,
-                                   _ptr(mean_rstd), _ptr(gamma) if want_coef else None, _ptr(beta) if want_coef else None,
-                                   _ptr(scale_shift) if want_coef else None, ss_stride, _ptr(coef), _stream()), "kd_gn_finalize_oct")
+    extra = (_ptr(gamma) if want_coef else None, _ptr(beta) if want_coef else None, _ptr(scale_shift) if want_coef else None, ss_stride,
+             _ptr(coef), _stream())
+    fused = FUSED_REDUCE and stats_a._reduced is None and (stats_b is None or stats_b._reduced is None)
+    if fused:  # reduce + finalize in one launch
+        L = lib()
+        n_a = L.kd_oct_reduce_splits(stats_a.rpt, stats_a.tiles, stats_a.TB) * stats_a.n_oct
+        n_b = 0 if stats_b is None else L.kd_oct_reduce_splits(stats_b.rpt, stats_b.tiles, stats_b.TB) * stats_b.n_oct
+        scratch = torch.empty((B * (n_a + n_b) * 2,), device=dev, dtype=torch.float32)
+        sb_args = (None, 0, 0, 0, 0) if stats_b is None else (_ptr(stats_b.partial), stats_b.rpt, stats_b.tiles, stats_b.TB, stats_b.n_oct)
+        check(L.kd_gn_reduce_finalize(_ptr(stats_a.partial), stats_a.rpt, stats_a.tiles, stats_a.TB, stats_a.n_oct, scale_a, *sb_args, scale_b,
+                                      B, num_groups, group_size, float(count), eps, _ptr(scratch), _ptr(_arrival_counters(dev, B)),
+                                      _ptr(mean_rstd), *extra), "kd_gn_reduce_finalize")
+    else:
+        sa = stats_a.reduced()
+        sb = stats_b.reduced() if stats_b is not None else None
+        check(lib().kd_gn_finalize_oct(_ptr(sa), stats_a.n_oct, stats_a.ns, scale_a, _ptr(sb), 0 if stats_b is None else stats_b.n_oct,
+                                       0 if stats_b is None else stats_b.ns, scale_b, B, num_groups, group_size, float(count), eps,
+                                       _ptr(mean_rstd), *extra), "kd_gn_finalize_oct")
     _count()
     return (mean_rstd, coef) if want_coef else mean_rstd
+
+
+_COUNTERS = {}
+
+
+def _arrival_counters(device, n):
+    """Zeroed, self-resetting arrival counters of the 'last block finalizes' kernels (one per batch image)."""
+    key = str(device)
+    t = _COUNTERS.get(key)
+    if t is None or t.numel() < n:
+        t = _COUNTERS[key] = torch.zeros((max(4096, n),), device=device, dtype=torch.int32)
+    return t
 
 
 def conv_pre_supported(B, H, W, Ca, Cb, Cout, ksize=3):

@@ -670,3 +670,37 @@ def test_conv_fused_groupnorm_preactivation(cuda_lib, B, H, W, Ca, Cb, Cout, use
     ov = got.double().cpu().view(B, H * W, Cout // 8, 8)
     exact = torch.stack((ov.sum(dim=(1, 3)), (ov * ov).sum(dim=(1, 3))), dim=-1)
     assert float(((st - exact).abs() / (exact.abs() + 1.0)).max()) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,Ca,Cb", [(2, 32, 32, 128, 0), (3, 40, 24, 64, 192), (1, 128, 64, 256, 128)])
+def test_reduce_finalize_single_launch_bit_identical(cuda_lib, B, H, W, Ca, Cb):
+    """kd_gn_reduce_finalize (last block of an image finalizes) == kd_oct_reduce + kd_gn_finalize_oct, bit for bit, on statistics
+    from the conv epilogue (source a) and from the standalone pass (source b); repeated launches reuse the arrival counters."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(Ca + Cb + H)
+    C, G = Ca + Cb, 8
+    x = nhwc(torch.randn(B, 64, H, W, generator=g))
+    w = bf(torch.randn(Ca, 9 * 64, generator=g) / 24).to(DEV)
+    xa = ops.conv_gemm(x, w, None, ksize=3, want_stats=True)
+    xb = nhwc(torch.randn(B, Cb, H, W, generator=g)) if Cb else None
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    ss = (torch.randn(B, 2 * C, generator=g) * 0.3).to(DEV)
+
+    def run(fused):
+        ops.FUSED_REDUCE = fused
+        try:
+            for t in (xa, xb):
+                if t is not None and getattr(t, "_kd_stats", None) is not None:
+                    t._kd_stats._reduced = None
+            if xb is not None and not hasattr(xb, "_kd_stats"):
+                xb._kd_stats = ops.oct_stats(xb)
+            return ops.gn_finalize_oct(ops.stats_of(xa), 1.0, ops.stats_of(xb) if Cb else None, 0.5, C // G, G, count=(C // G) * H * W,
+                                       gamma=gamma, beta=beta, scale_shift=ss, want_coef=True)
+        finally:
+            ops.FUSED_REDUCE = True
+
+    mr0, cf0 = run(False)
+    for _ in range(3):
+        mr1, cf1 = run(True)
+        assert torch.equal(mr0, mr1) and torch.equal(cf0, cf1)
