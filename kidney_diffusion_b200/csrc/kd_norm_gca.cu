@@ -365,14 +365,12 @@ __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __r
   const long p1 = p0 + per < HW ? p0 + per : HW;
   const long base = (long)b * HW * C + (long)o * 8;
   float s1 = 0.f, s2 = 0.f;
-  for (long p = p0 + pl; p < p1; p += lanes) {
-    int4 raw = ld_stream(h + base + p * C);
+  auto body = [&](long p, const int4& raw, const int4& rr) {
     float v[8];
-    h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
+    h16x8_to_float(*reinterpret_cast<const h16x8*>(&raw), v);
     if (res != nullptr) {
-      int4 rr = ld_stream(res + base + p * C);
       float r[8];
-      h16x8_to_float(*reinterpret_cast<h16x8*>(&rr), r);
+      h16x8_to_float(*reinterpret_cast<const h16x8*>(&rr), r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], g[j], r[j]);
     } else {
@@ -380,7 +378,7 @@ __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __r
       for (int j = 0; j < 8; ++j) v[j] *= g[j];
     }
     h16x8 o8 = float_to_h16x8(v);
-    *reinterpret_cast<int4*>(out + base + p * C) = *reinterpret_cast<int4*>(&o8);
+    st_stream(out + base + p * C, *reinterpret_cast<int4*>(&o8));
     if (oct_partial != nullptr) {  // statistics of the rounded values that were stored
       float f[8];
       h16x8_to_float(o8, f);
@@ -390,6 +388,23 @@ __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __r
         s2 = fmaf(f[j], f[j], s2);
       }
     }
+  };
+  long p = p0 + pl;
+  // four pixels per step, all loads first; the per-thread accumulation order is unchanged
+  for (; p + 3L * lanes < p1; p += 4L * lanes) {
+    int4 raw[4], rr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      raw[u] = ld_stream(h + base + (p + (long)u * lanes) * C);
+      rr[u] = res != nullptr ? ld_stream(res + base + (p + (long)u * lanes) * C) : make_int4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(p + (long)u * lanes, raw[u], rr[u]);
+  }
+  for (; p < p1; p += lanes) {
+    const int4 raw = ld_stream(h + base + p * C);
+    const int4 rr = res != nullptr ? ld_stream(res + base + p * C) : make_int4(0, 0, 0, 0);
+    body(p, raw, rr);
   }
   if (oct_partial != nullptr) {
     sm[threadIdx.x * 2] = s1;
