@@ -204,9 +204,13 @@ int kd_im2col_nchw(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int
 int kd_init_conv_kp(int C, int ksize);
 int kd_init_conv(const float* x /* fp32 [B,C,H,W] */, int B, int C, int H, int W, int ksize, const void* w_packed, const float* bias,
                  const void* addend, void* out /* fp16 [B,H,W,Cout] */, int Cout, kd_stream_t stream);
+/* w_split: the Ca-channel part of the filter pre-split into fp16 hi + lo for the tensor cores, kd_final_conv_pack_elems(Ca)
+ * fp16 elements written once per model by kd_final_conv_pack. */
+long kd_final_conv_pack_elems(int Ca);
+int kd_final_conv_pack(const float* w /* fp32 [Cout][3][3][Ca+Cb] */, int Cout, int Ca, int Cb, void* w_split, kd_stream_t stream);
 int kd_final_conv(const void* xa /* fp16 [B,H,W,Ca] */, int Ca, const float* xb /* fp32 NCHW [B,Cb,H,W] or NULL */, int Cb,
-                  const float* w /* fp32 [Cout][3][3][Ca+Cb] */, const float* bias, float* out /* fp32 NCHW [B,Cout,H,W] */, int B,
-                  int H, int W, int Cout, kd_stream_t stream);
+                  const float* w /* fp32 [Cout][3][3][Ca+Cb] */, const void* w_split, const float* bias,
+                  float* out /* fp32 NCHW [B,Cout,H,W] */, int B, int H, int W, int Cout, kd_stream_t stream);
 
 /* ------------------------------------------------------------------ K6 / K7: sampler update
  * replaces: Imagen.p_mean_variance + p_sample (x0 from eps / v, dynamic threshold = torch.quantile(|x0|, 0.95) per sample,

@@ -75,74 +75,109 @@ __device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, ui
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// filter pre-split for the tensor cores, once per model: [chunk][hi | lo][tap][n = 8][FC_WK] fp16 (rows n >= Cout and the
+// k padding are zero), so a block fetches a chunk's filter with 720 16-byte copies instead of 864 scalar loads + splits
+constexpr int FC_WCHUNK = 2 * 9 * 8 * FC_WK;  // h16 elements per 32-channel chunk (11 520 B)
+
+__global__ void final_conv_pack_kernel(const float* __restrict__ w, int Cout, int Ca, int Ctot, h16* __restrict__ wp) {
+  const int total = (Ca / FC_CH) * FC_WCHUNK;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % FC_WK, n = (i / FC_WK) % 8, tap = (i / (FC_WK * 8)) % 9, part = (i / (FC_WK * 72)) % 2, chunk = i / FC_WCHUNK;
+    float v = 0.f;
+    if (k < FC_CH && n < Cout) {
+      const float wf = w[((long)n * 9 + tap) * Ctot + chunk * FC_CH + k];
+      const h16 hi = __float2half_rn(wf);
+      v = part == 0 ? __half2float(hi) : wf - __half2float(hi);
+    }
+    wp[i] = __float2half_rn(v);
+  }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled (conv padding)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
 __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb,
-                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                         float* __restrict__ out, int H, int W, int Cout) {
-  __shared__ __align__(16) h16 s_act[FC_HH * FC_HW * FC_PIX_STRIDE];
-  __shared__ __align__(16) h16 s_w[2][9][8][FC_WK];  // [hi / lo][tap][n][k]
-  __shared__ float s_xb[4 * FC_HH * FC_HW];
-  __shared__ float s_wb[FC_MAXCO * 9 * 4];
-  __shared__ float s_res[FC_MAXCO][FC_TH][FC_TW];
+                                                         const float* __restrict__ w, const h16* __restrict__ wp,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                                                         int Cout) {
+  extern __shared__ __align__(16) uint8_t fc_smem[];
+  constexpr int ACT_BYTES = FC_HH * FC_HW * FC_PIX_STRIDE * 2;  // 27 200
+  constexpr int W_BYTES = FC_WCHUNK * 2;                       // 11 520
+  // [2 x activations][2 x filter] double-buffered by cp.async, then the fp32 tails
+  h16* s_w_base = reinterpret_cast<h16*>(fc_smem + 2 * ACT_BYTES);
+  float* s_xb = reinterpret_cast<float*>(fc_smem + 2 * ACT_BYTES + 2 * W_BYTES);
+  float* s_wb = s_xb + 4 * FC_HH * FC_HW;
+  float* s_res = s_wb + FC_MAXCO * 9 * 4;  // [FC_MAXCO][FC_TH][FC_TW]
+  const uint32_t s_u32 = (uint32_t)__cvta_generic_to_shared(fc_smem);
   const int Ctot = Ca + Cb;
   const int b = blockIdx.z, h0 = blockIdx.y * FC_TH, w0 = blockIdx.x * FC_TW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 
-  // rows of the filter tile that no output channel uses stay zero
-  for (int i = threadIdx.x; i < 2 * 9 * 8 * FC_WK; i += 256) (&s_w[0][0][0][0])[i] = __float2half(0.f);
-
-  // ldmatrix lane addressing of an m16 x k16 A fragment: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
-  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
-  const int a_kof = (lane >> 4) * 8;
-  const uint32_t s_act_u32 = (uint32_t)__cvta_generic_to_shared(s_act);
-
-  for (int c0 = 0; c0 < Ca; c0 += FC_CH) {
-    __syncthreads();
+  auto issue_chunk = [&](int chunk, int buf) {
+    const uint32_t act_dst = s_u32 + buf * ACT_BYTES;
     for (int i = threadIdx.x; i < FC_HH * FC_HW * 4; i += 256) {
       const int v = i & 3, pix = i >> 2;
       const int py = pix / FC_HW, px = pix % FC_HW;
       const int gy = h0 + py - 1, gx = w0 + px - 1;
-      int4 val = make_int4(0, 0, 0, 0);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) val = ld_stream(xa + (((long)b * H + gy) * W + gx) * Ca + c0 + v * 8);
-      *reinterpret_cast<int4*>(&s_act[pix * FC_PIX_STRIDE + v * 8]) = val;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const h16* src = xa + (((long)b * H + (ok ? gy : 0)) * W + (ok ? gx : 0)) * Ca + chunk * FC_CH + v * 8;
+      cp_async16(act_dst + (pix * FC_PIX_STRIDE + v * 8) * 2, src, ok);
     }
-    for (int i = threadIdx.x; i < Cout * 9 * FC_CH; i += 256) {
-      const int c = i % FC_CH, tap = (i / FC_CH) % 9, co = i / (FC_CH * 9);
-      const float wf = w[((long)co * 9 + tap) * Ctot + c0 + c];
-      const h16 hi = __float2half_rn(wf);
-      s_w[0][tap][co][c] = hi;
-      s_w[1][tap][co][c] = __float2half_rn(wf - __half2float(hi));
+    const uint32_t w_dst = s_u32 + 2 * ACT_BYTES + buf * W_BYTES;
+    const h16* wsrc = wp + (long)chunk * FC_WCHUNK;
+    for (int i = threadIdx.x; i < W_BYTES / 16; i += 256) cp_async16(w_dst + i * 16, wsrc + i * 8, true);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ldmatrix lane addressing of an m16 x k16 A fragment: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_kof = (lane >> 4) * 8;
+  const int n_chunks = Ca / FC_CH;
+  issue_chunk(0, 0);
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int buf = chunk & 1;
+    if (chunk + 1 < n_chunks) {
+      issue_chunk(chunk + 1, buf ^ 1);  // the buffer was released by the barrier that ended chunk - 1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const uint32_t act_u32 = s_u32 + buf * ACT_BYTES;
+    const h16* sw = s_w_base + buf * FC_WCHUNK;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int py = warp + tap / 3, dx = tap % 3;
 #pragma unroll
       for (int ks = 0; ks < FC_CH / 16; ++ks) {
-        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&s_w[0][tap][lane >> 2][ks * 16 + (lane & 3) * 2]);
-        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&s_w[0][tap][lane >> 2][ks * 16 + 8 + (lane & 3) * 2]);
-        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&s_w[1][tap][lane >> 2][ks * 16 + (lane & 3) * 2]);
-        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&s_w[1][tap][lane >> 2][ks * 16 + 8 + (lane & 3) * 2]);
+        const h16* wh = sw + ((0 * 9 + tap) * 8 + (lane >> 2)) * FC_WK + ks * 16 + (lane & 3) * 2;
+        const h16* wl = sw + ((1 * 9 + tap) * 8 + (lane >> 2)) * FC_WK + ks * 16 + (lane & 3) * 2;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh), bh1 = *reinterpret_cast<const uint32_t*>(wh + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl), bl1 = *reinterpret_cast<const uint32_t*>(wl + 8);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           uint32_t a0, a1, a2, a3;
           const int px = mt * 16 + a_row + dx;
-          ldmatrix_x4(s_act_u32 + ((py * FC_HW + px) * FC_PIX_STRIDE + ks * 16 + a_kof) * 2, a0, a1, a2, a3);
+          ldmatrix_x4(act_u32 + ((py * FC_HW + px) * FC_PIX_STRIDE + ks * 16 + a_kof) * 2, a0, a1, a2, a3);
           mma_16816(acc[mt], a0, a1, a2, a3, bh0, bh1);
           mma_16816(acc[mt], a0, a1, a2, a3, bl0, bl1);
         }
       }
     }
+    __syncthreads();
   }
   // accumulator fragment: rows lane/4 and lane/4 + 8 of the m-tile, columns (lane%4)*2 + {0, 1}
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     const int n0 = (lane & 3) * 2, r = lane >> 2;
     if (n0 < FC_MAXCO) {
-      s_res[n0][warp][mt * 16 + r] = acc[mt][0];
-      s_res[n0 + 1][warp][mt * 16 + r] = acc[mt][1];
-      s_res[n0][warp][mt * 16 + r + 8] = acc[mt][2];
-      s_res[n0 + 1][warp][mt * 16 + r + 8] = acc[mt][3];
+      s_res[(n0 * FC_TH + warp) * FC_TW + mt * 16 + r] = acc[mt][0];
+      s_res[((n0 + 1) * FC_TH + warp) * FC_TW + mt * 16 + r] = acc[mt][1];
+      s_res[(n0 * FC_TH + warp) * FC_TW + mt * 16 + r + 8] = acc[mt][2];
+      s_res[((n0 + 1) * FC_TH + warp) * FC_TW + mt * 16 + r + 8] = acc[mt][3];
     }
   }
   const int ty = threadIdx.x / FC_TW, tx = threadIdx.x % FC_TW;
@@ -175,9 +210,11 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__
   if (gy < H && gx < W) {
 #pragma unroll
     for (int co = 0; co < FC_MAXCO; ++co)
-      if (co < Cout) out[(((long)b * Cout + co) * H + gy) * W + gx] = s_res[co][ty][tx] + extra[co] + (bias ? bias[co] : 0.f);
+      if (co < Cout) out[(((long)b * Cout + co) * H + gy) * W + gx] = s_res[(co * FC_TH + ty) * FC_TW + tx] + extra[co] + (bias ? bias[co] : 0.f);
   }
 }
+
+constexpr int FC_SMEM = 2 * (FC_HH * FC_HW * FC_PIX_STRIDE * 2) + 2 * (FC_WCHUNK * 2) + (4 * FC_HH * FC_HW + FC_MAXCO * 9 * 4 + FC_MAXCO * FC_TH * FC_TW) * 4;
 
 }  // namespace
 
@@ -200,16 +237,32 @@ extern "C" int kd_im2col_nchw(const float* x, int B, int C, int H, int W, int ks
   return KD_OK;
 }
 
-extern "C" int kd_final_conv(const void* xa, int Ca, const float* xb, int Cb, const float* w, const float* bias, float* out, int B,
-                             int H, int W, int Cout, kd_stream_t stream_) {
+extern "C" long kd_final_conv_pack_elems(int Ca) { return (long)(Ca / FC_CH) * FC_WCHUNK; }
+
+extern "C" int kd_final_conv_pack(const float* w, int Cout, int Ca, int Cb, void* w_split, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(xa && w && out && B > 0 && H > 0 && W > 0, "kd_final_conv: bad argument");
+  KD_REQUIRE(w && w_split && Cout >= 1 && Cout <= FC_MAXCO && Ca > 0 && Ca % FC_CH == 0 && Cb >= 0, "kd_final_conv_pack: bad argument");
+  final_conv_pack_kernel<<<64, 256, 0, stream>>>(w, Cout, Ca, Ca + Cb, reinterpret_cast<h16*>(w_split));
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_final_conv(const void* xa, int Ca, const float* xb, int Cb, const float* w, const void* w_split, const float* bias,
+                             float* out, int B, int H, int W, int Cout, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(xa && w && w_split && out && B > 0 && H > 0 && W > 0, "kd_final_conv: bad argument");
   KD_REQUIRE(Ca > 0 && Ca % FC_CH == 0, "kd_final_conv: Ca=%d must be a multiple of %d", Ca, FC_CH);
   KD_REQUIRE(Cb >= 0 && Cb <= 4 && (Cb == 0 || xb), "kd_final_conv: Cb must be <= 4");
   KD_REQUIRE(Cout >= 1 && Cout <= FC_MAXCO, "kd_final_conv: Cout must be <= %d", FC_MAXCO);
   KD_REQUIRE(kd_ceil_div(H, FC_TH) <= 65535 && B <= 65535, "kd_final_conv: grid too large");
+  static bool configured = false;
+  if (!configured) {
+    KD_CUDA(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    configured = true;
+  }
   dim3 grid(kd_ceil_div(W, FC_TW), kd_ceil_div(H, FC_TH), B);
-  final_conv_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const h16*>(xa), Ca, xb, Cb, w, bias, out, H, W, Cout);
+  final_conv_kernel<<<grid, 256, FC_SMEM, stream>>>(reinterpret_cast<const h16*>(xa), Ca, xb, Cb, w, reinterpret_cast<const h16*>(w_split), bias,
+                                                    out, H, W, Cout);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -548,7 +548,12 @@ def final_conv(xa, xb, w, bias):
     Cb = 0 if xb is None else xb.shape[1]
     Cout = w.shape[0]
     out = torch.empty((B, Cout, H, W), device=xa.device, dtype=torch.float32)
-    check(lib().kd_final_conv(_ptr(xa), Ca, _ptr(xb), Cb, _ptr(w), _ptr(bias), _ptr(out), B, H, W, Cout, _stream()), "kd_final_conv")
+    ws = getattr(w, "_kd_split", None)
+    if ws is None:  # one-time hi + lo fp16 split of the filter (cached on the weight tensor)
+        ws = torch.empty((lib().kd_final_conv_pack_elems(Ca),), device=xa.device, dtype=ACT_DTYPE)
+        check(lib().kd_final_conv_pack(_ptr(w), Cout, Ca, Cb, _ptr(ws), _stream()), "kd_final_conv_pack")
+        w._kd_split = ws
+    check(lib().kd_final_conv(_ptr(xa), Ca, _ptr(xb), Cb, _ptr(w), _ptr(ws), _ptr(bias), _ptr(out), B, H, W, Cout, _stream()), "kd_final_conv")
     _count()
     return out
 
