@@ -108,7 +108,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        mbar_wait_relaxed(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, STAGE_BYTES);
         const int tap = kb / p.chunks_per_tap;
@@ -468,7 +468,7 @@ __device__ __forceinline__ void pair_epilogue_role(const ConvParams& p, const CU
       }
     }
 
-    mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+    mbar_wait_relaxed(smem_u32(&tmem_full_bar[as]), aph);
     tc_fence_after();
     if (p.out_f32) {
       // fp32 output (tests / small tensors): direct per-row stores
@@ -712,7 +712,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          mbar_wait_relaxed(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb_local = smem_u32(&full_bar[s]);
           const uint32_t fb_leader = fb_local & kPeerBitMask;
           const int tap = kb / p.chunks_per_tap;
@@ -886,7 +886,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           for (int tg = 0; tg < 9 / TPS; ++tg, ++itb) {
             const uint32_t sb = itb % BS;
             const uint32_t phb = (itb / BS) & 1;
-            mbar_wait(smem_u32(&b_empty[sb]), phb ^ 1u);
+            mbar_wait_relaxed(smem_u32(&b_empty[sb]), phb ^ 1u);
             const uint32_t fb_local = smem_u32(&b_full[sb]);
             if (rank == 0) mbar_expect_tx(fb_local, 2 * B_STAGE);
 #pragma unroll
@@ -914,7 +914,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++ita) {
           const uint32_t sa = ita % AS;
           const uint32_t pha = (ita / AS) & 1;
-          mbar_wait(smem_u32(&a_empty[sa]), pha ^ 1u);
+          mbar_wait_relaxed(smem_u32(&a_empty[sa]), pha ^ 1u);
           const uint32_t fa_local = smem_u32(&a_full[sa]);
           const bool src_b = ch >= p.chunks_a;
           const CUtensorMap* map = src_b ? &map_b : &map_a;
@@ -1007,7 +1007,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             cf[j].x *= 0.5f; cf[j].y *= 0.5f; cf[j].z *= 0.5f; cf[j].w *= 0.5f;
           }
         }
-        mbar_wait(smem_u32(&a_full[sa]), pha);
+        mbar_wait_relaxed(smem_u32(&a_full[sa]), pha);
         if (live) {
           const uint32_t col = a_base + sa * HALO_STAGE_BYTES + (uint32_t)pu * 16u;
           // three units per step, all loads first: 24 independent FMA -> SiLU chains keep the MUFU pipe busy (one unit at a

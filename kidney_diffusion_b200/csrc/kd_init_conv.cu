@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
         for (int pl = 0; pl < passes; ++pl) {
           for (int j = 0; j < p.n_chunks; ++j, ++cc) {
             const int s = cc % IC_BSTAGES;
-            mbar_wait(smem_u32(&b_empty[s]), ((cc / IC_BSTAGES) & 1) ^ 1u);
+            mbar_wait_relaxed(smem_u32(&b_empty[s]), ((cc / IC_BSTAGES) & 1) ^ 1u);
             const uint32_t fb = smem_u32(&b_full[s]);
             mbar_expect_tx(fb, B_STAGE_BYTES);
             tma_load_2d(smem_base + s * B_STAGE_BYTES, &map_w, fb, j * 64, 0);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
 #pragma unroll
           for (int g = 0; g < BN / 8; ++g) add[g] = *reinterpret_cast<const int4*>(p.addend + off + g * 8);  // may alias out
         }
-        mbar_wait(smem_u32(&tmem_full[a]), ph);
+        mbar_wait_relaxed(smem_u32(&tmem_full[a]), ph);
         tc_fence_after();
         // 64-channel halves are transposed through a per-warp 4 KB staging tile (16-byte units XOR-swizzled by pixel) so that
         // every global store instruction writes four whole 128-byte pixel-halves
@@ -247,11 +247,11 @@ __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_c
         if (pl == 0) {
           rr0 = 0;
           nrows = p.ks + 1;
-          if (q >= 1) mbar_wait(smem_u32(&tmem_full[(q - 1) & 1]), ((q - 1) >> 1) & 1);
+          if (q >= 1) mbar_wait_relaxed(smem_u32(&tmem_full[(q - 1) & 1]), ((q - 1) >> 1) & 1);
         } else {
           rr0 = 2 * pl + p.ks - 1;
           nrows = 2;
-          if (q >= 2) mbar_wait(smem_u32(&tmem_full[q & 1]), ((q - 2) >> 1) & 1);
+          if (q >= 2) mbar_wait_relaxed(smem_u32(&tmem_full[q & 1]), ((q - 2) >> 1) & 1);
         }
         const int total = nrows * units_per_row;
         for (int i = f; i < total; i += IC_FILL_THREADS) {

@@ -35,6 +35,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for waits that are expected to be long and are not on the MMA issue path (producers waiting for a free slot, epilogue
+// warps waiting for an accumulator, transform warps waiting for a tile): back off between polls so the spinning warps do
+// not burn issue slots and power -- the GPU runs power-capped under this load
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 // one lane of a fully converged warp (tcgen05.mma / commit are single-thread instructions; keeping the surrounding loop
 // warp-convergent lets the compiler hold descriptors in uniform registers instead of a per-MMA R2UR waterfall loop)
 __device__ __forceinline__ bool elect_one() {
