@@ -1,16 +1,19 @@
 // K1: implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA).
 //
-//   M = B*H*W output pixels (tile = TB x TH x TW = 128 pixels), N = Cout, K = taps * (Ca + Cb).
-//   A operand: for k-block (tap, 64-channel chunk) one TMA tiled load of a [TB,TH,TW,64] box of the NHWC h16
-//              activation tensor, shifted by the tap offset; out-of-bounds coordinates are zero-filled by the TMA unit,
-//              which implements the convolution's zero padding.  The box lands in shared memory as 128 rows x 128 B with
-//              the 128-byte swizzle, i.e. exactly the canonical K-major SWIZZLE_128B UMMA operand layout.
-//   B operand: [BN, 64] box of the packed weight matrix [Cout, K] (K-major), same swizzle.
-//   D        : 128 x BN fp32 accumulator in tensor memory; read back by 4 epilogue warps with tcgen05.ld.
+//   M = B*H*W output pixels, N = Cout, K = taps * (Ca + Cb); A = NHWC fp16 activations (one or two concatenated sources),
+//   B = packed weights [Cout, K] (K-major, K ordered (tap, channel)); D = fp32 accumulator in tensor memory.
+//   Both operands land in shared memory through TMA with the 128-byte swizzle, i.e. as canonical K-major SWIZZLE_128B UMMA
+//   operands; out-of-bounds TMA coordinates are zero-filled, which implements the convolution's zero padding.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).  Two CTAs are resident per SM (3-stage ring,
-// <= 100 KB smem each, 128 TMEM columns each) so one CTA's epilogue overlaps the other CTA's main loop.
+// Three kernels share the PTX wrappers of kd_tc.cuh:
+//   conv_gemm_kernel       128 x BN tile per CTA, 192 threads, 2 CTAs/SM            (Cout < 128: small models / tests)
+//   conv_gemm_pair_kernel  cta_group::2, UMMA M = 256, persistent, tap-loop A loads  (1x1, 2x2-stride-2, tiny images)
+//   conv_gemm_halo_kernel  as the pair kernel, but all nine taps of a 3x3 read ONE halo tile per 64-channel chunk, and the
+//                          GroupNorm + scale/shift + SiLU of the consuming Block can be applied to that tile in shared
+//                          memory (PRE)                                              (every 3x3 on >= 16 x 8 images)
+// and one epilogue (pair_epilogue_role): TMEM -> registers -> swizzled staging -> one TMA store per 128 x 64 item, with
+// fused bias / activation / gated residual (addend tile TMA-loaded one item ahead) / GroupNorm octet statistics /
+// GlobalContext logits.  MMA issue loops are warp-convergent with one elected lane (uniform-register descriptors).
 #include <cuda.h>
 #include <mutex>
 
