@@ -508,6 +508,33 @@ __global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, in
   }
 }
 
+// per-lane share of the {sum, sumsq} of one GroupNorm group from the split sums of up to two concatenated sources: the
+// (octet, split) pairs of the group are dealt to the 32 lanes (independent loads in flight instead of a serial loop over up
+// to 64 splits), each lane adds its pairs in index order, the caller finishes with the fixed shuffle tree.  Used by both the
+// standalone and the single-launch finalize so that they stay bit-identical.
+__device__ __forceinline__ void group_octet_sums(int g, int lane, int group_size, const float* sa, int na, int nsa, float scale_a,
+                                                 const float* sb, int nb, int nsb, float scale_b, int b, double& s, double& ss) {
+  const int o0 = (g * group_size) >> 3, o1 = ((g + 1) * group_size) >> 3;  // octets of the group in concat order
+  const int a0 = o0 < na ? o0 : na, a1 = o1 < na ? o1 : na;                // ... that fall into source a
+  const int items_a = (a1 - a0) * nsa;
+  for (int i = lane; i < items_a; i += 32) {
+    const int o = a0 + i / nsa, k = i - (i / nsa) * nsa;
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(sa) + ((long)b * nsa + k) * na + o);
+    s += (double)v.x * scale_a;
+    ss += (double)v.y * scale_a * scale_a;
+  }
+  if (nb > 0) {
+    const int b0 = (o0 > na ? o0 : na) - na, b1 = (o1 > na ? o1 : na) - na;
+    const int items_b = (b1 - b0) * nsb;
+    for (int i = lane; i < items_b; i += 32) {
+      const int o = b0 + i / nsb, k = i - (i / nsb) * nsb;
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(sb) + ((long)b * nsb + k) * nb + o);
+      s += (double)v.x * scale_b;
+      ss += (double)v.y * scale_b * scale_b;
+    }
+  }
+}
+
 // mean / rstd per (b, group) from reduced octet sums of up to two concatenated sources: one warp per group
 __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int nsa, float scale_a, const float* __restrict__ sb, int nb,
                                        int nsb, float scale_b, int G, int group_size, double count, float eps,
@@ -518,22 +545,7 @@ __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
   double s = 0.0, ss = 0.0;
-  for (int o = lane; o < na + nb; o += 32) {
-    if ((o * 8) / group_size != g) continue;
-    if (o < na) {
-      for (int k = 0; k < nsa; ++k) {
-        const float2 v = reinterpret_cast<const float2*>(sa)[((long)b * nsa + k) * na + o];
-        s += (double)v.x * scale_a;
-        ss += (double)v.y * scale_a * scale_a;
-      }
-    } else {
-      for (int k = 0; k < nsb; ++k) {
-        const float2 v = reinterpret_cast<const float2*>(sb)[((long)b * nsb + k) * nb + (o - na)];
-        s += (double)v.x * scale_b;
-        ss += (double)v.y * scale_b * scale_b;
-      }
-    }
-  }
+  group_octet_sums(g, lane, group_size, sa, na, nsa, scale_a, sb, nb, nsb, scale_b, b, s, ss);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -629,22 +641,7 @@ __global__ void __launch_bounds__(256) gn_reduce_finalize_kernel(const OctSrc a,
   const int na = a.n_oct, nb = b2.NS > 0 ? b2.n_oct : 0;
   for (int g = threadIdx.x >> 5; g < G; g += 8) {
     double s = 0.0, ss = 0.0;
-    for (int o = lane; o < na + nb; o += 32) {
-      if ((o * 8) / group_size != g) continue;
-      if (o < na) {
-        for (int k = 0; k < a.NS; ++k) {
-          const float2 v = __ldcg(reinterpret_cast<const float2*>(a.out) + ((long)b * a.NS + k) * na + o);
-          s += (double)v.x * a.scale;
-          ss += (double)v.y * a.scale * a.scale;
-        }
-      } else {
-        for (int k = 0; k < b2.NS; ++k) {
-          const float2 v = __ldcg(reinterpret_cast<const float2*>(b2.out) + ((long)b * b2.NS + k) * nb + (o - na));
-          s += (double)v.x * b2.scale;
-          ss += (double)v.y * b2.scale * b2.scale;
-        }
-      }
-    }
+    group_octet_sums(g, lane, group_size, a.out, na, a.NS, a.scale, b2.out, nb, b2.NS, b2.scale, b, s, ss);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       s += __shfl_xor_sync(0xffffffffu, s, off);
