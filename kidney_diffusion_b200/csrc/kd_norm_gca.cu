@@ -489,9 +489,20 @@ __global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, in
   const long r0 = (long)sp * per, r1 = (r0 + per < count) ? r0 + per : count;
   double s1 = 0.0, s2 = 0.0;
   const float2* pp = reinterpret_cast<const float2*>(partial);
-  for (long i = r0 + l; i < r1; i += lanes) {
-    const long row = ((long)tile_b * tiles + i / rpb) * rpt + (long)sub * rpb + i % rpb;
-    const float2 v = pp[row * n_oct + o];
+  auto row_of = [&](long i) { return ((long)tile_b * tiles + i / rpb) * rpt + (long)sub * rpb + i % rpb; };
+  long i = r0 + l;
+  for (; i + 7L * lanes < r1; i += 8L * lanes) {
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(pp + row_of(i + (long)u * lanes) * n_oct + o);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s1 += v[u].x;
+      s2 += v[u].y;
+    }
+  }
+  for (; i < r1; i += lanes) {
+    const float2 v = __ldg(pp + row_of(i) * n_oct + o);
     s1 += v.x;
     s2 += v.y;
   }
@@ -609,9 +620,21 @@ __global__ void __launch_bounds__(256) gn_reduce_finalize_kernel(const OctSrc a,
     double s1 = 0.0, s2 = 0.0;
     if (l < lanes) {
       const float2* pp = reinterpret_cast<const float2*>(s.partial);
-      for (long i = r0 + l; i < r1; i += lanes) {
-        const long row = ((long)tile_b * s.tiles + i / rpb) * s.rpt + (long)sub * rpb + i % rpb;
-        const float2 v = pp[row * n_oct + o];
+      auto row_of = [&](long i) { return ((long)tile_b * s.tiles + i / rpb) * s.rpt + (long)sub * rpb + i % rpb; };
+      long i = r0 + l;
+      // eight rows in flight per thread (the loop was one exposed L2 / HBM latency per row); added in the same order
+      for (; i + 7L * lanes < r1; i += 8L * lanes) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(pp + row_of(i + (long)u * lanes) * n_oct + o);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          s1 += v[u].x;
+          s2 += v[u].y;
+        }
+      }
+      for (; i < r1; i += lanes) {
+        const float2 v = __ldg(pp + row_of(i) * n_oct + o);
         s1 += v.x;
         s2 += v.y;
       }
@@ -864,9 +887,9 @@ extern "C" int kd_oct_stats(const void* x, int B, long HW, int C, float* partial
 extern "C" int kd_oct_reduce_splits(int rpt, int tiles, int TB) {
   if (rpt <= 0 || tiles <= 0 || TB <= 0) return 0;
   const long count = (long)tiles * (rpt / TB);
-  long ns = count / 32;
+  long ns = count / 64;  // >= 64 partial rows per split, at most one split per SM
   if (ns < 1) ns = 1;
-  if (ns > 64) ns = 64;
+  if (ns > 144) ns = 144;
   return (int)ns;
 }
 

@@ -111,7 +111,7 @@ class OctStats:
         self._reduced = None
 
     def reduced(self):
-        """[B, NS, C/8, 2] split sums (NS <= 64 row ranges per image; kd_gn_finalize_oct adds them in fixed order)."""
+        """[B, NS, C/8, 2] split sums (NS <= 144 row ranges per image; kd_gn_finalize_oct adds them in fixed order)."""
         if self._reduced is None:
             self.ns = lib().kd_oct_reduce_splits(self.rpt, self.tiles, self.TB)
             out = torch.empty((self.B, self.ns, self.n_oct, 2), device=self.partial.device, dtype=torch.float32)
