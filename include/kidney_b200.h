@@ -74,7 +74,8 @@ typedef struct KdConvDesc {
 } KdConvDesc;
 
 /* Test / profiling hook: 0 = automatic kernel choice (default), 1 = force the single-CTA 128x128 kernel, 2 = force the
- * CTA-pair (cta_group::2) kernel.  Both kernels accumulate each output in the same k order: results are bit-identical. */
+ * CTA-pair (cta_group::2) kernels (halo variant where it applies), 4 = CTA-pair tap-loop kernel only.  All kernels accumulate
+ * each output in the same k order: results are bit-identical. */
 int kd_set_conv_impl(int impl);
 
 int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,

@@ -29,7 +29,6 @@ constexpr int NUM_THREADS = 192;
 
 struct ConvParams {
   int mode, B, H, W, Ca, Cb, Cout, ksize, act, out_mode, out_f32, addend_f32;
-  int dbg_skip_a;  // timing experiment only (kd_set_conv_impl(3)): load the A tile for one tap in three
   int TW, TH, TB;
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int chunks_a, chunks_per_tap, num_kb;
@@ -719,15 +718,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint32_t fb_local = smem_u32(&full_bar[s]);
           const uint32_t fb_leader = fb_local & kPeerBitMask;
           const int tap = kb / p.chunks_per_tap;
-          const bool load_a = !p.dbg_skip_a || (tap % 3 == 0);
-          if (rank == 0) mbar_expect_tx(fb_local, 2 * (load_a ? STAGE_BYTES : B_HALF_BYTES));
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * STAGE_BYTES);
           const int ch = kb - tap * p.chunks_per_tap;
           const bool src_b = ch >= p.chunks_a;
           const CUtensorMap* map = src_b ? &map_b : &map_a;
           const int c0 = (src_b ? (ch - p.chunks_a) : ch) * BK;
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-          if (!load_a) {
-          } else if (p.mode == 1) {
+          if (p.mode == 1) {
             const int dy = tap >> 1, dx = tap & 1;
             const int C = src_b ? p.Cb : p.Ca;
             tma_load_5d_2sm(a_dst, map, fb_leader, dx * C + c0, w0, dy, h0, b0);
@@ -1250,8 +1247,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   return KD_OK;
 }
 
-int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = pair (halo where possible), 3 = tap-loop pair + skip-A timing
-                      // experiment, 4 = tap-loop pair kernel only (no halo reuse)
+int g_conv_impl = 0;  // 0 = auto, 1 = single-CTA kernel, 2 = pair (halo where possible), 4 = tap-loop pair kernel only (no halo)
 
 }  // namespace
 
@@ -1261,7 +1257,7 @@ int kd_encode_tiled_h16(CUtensorMap* m, const void* base, int rank, const uint64
 }
 
 extern "C" int kd_set_conv_impl(int impl) {
-  if (impl < 0 || impl > 4) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0..4");
+  if (impl < 0 || impl > 4 || impl == 3) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0, 1, 2 or 4");
   g_conv_impl = impl;
   return KD_OK;
 }
@@ -1274,8 +1270,8 @@ struct Tiling {
 };
 Tiling choose_tiling(const KdConvDesc* d) {
   Tiling t;
-  t.use_pair = (g_conv_impl == 2) || (g_conv_impl == 4) || ((g_conv_impl == 0 || g_conv_impl == 3) && d->Cout >= 128);
-  t.use_halo = t.use_pair && g_conv_impl != 4 && g_conv_impl != 3 && d->mode == 0 && d->ksize == 3 && d->H >= HALO_TH &&
+  t.use_pair = (g_conv_impl == 2) || (g_conv_impl == 4) || (g_conv_impl == 0 && d->Cout >= 128);
+  t.use_halo = t.use_pair && g_conv_impl != 4 && d->mode == 0 && d->ksize == 3 && d->H >= HALO_TH &&
                d->W >= HALO_TW && !d->out_f32 && d->out_mode == 0;
   if (t.use_halo) {
     t.TW = HALO_TW; t.TH = HALO_TH; t.TB = 1;
@@ -1337,36 +1333,19 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
   p.B = d->B; p.H = d->H; p.W = d->W; p.Ca = d->Ca; p.Cb = d->Cb; p.Cout = d->Cout;
   p.ksize = (d->mode == 0) ? d->ksize : 1;
   p.act = d->act; p.out_mode = d->out_mode; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
-  p.TH = pow2_ceil(d->H) < 8 ? pow2_ceil(d->H) : 8;
-  {
-    const int wmax = BM / p.TH;
-    p.TW = pow2_ceil(d->W) < wmax ? pow2_ceil(d->W) : wmax;
-  }
-  p.TB = BM / (p.TH * p.TW);
-  p.tiles_w = kd_ceil_div(d->W, p.TW);
-  p.tiles_h = kd_ceil_div(d->H, p.TH);
-  p.tiles_b = kd_ceil_div(d->B, p.TB);
+  // kernel choice (one place: choose_tiling): CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else
+  // the single-CTA kernel; 3x3 convolutions on images of at least 16 x 8 pixels use the halo-reuse variant
+  const Tiling tl = choose_tiling(d);
+  const bool use_pair = tl.use_pair, use_halo = tl.use_halo;
+  KD_REQUIRE(!((g_conv_impl == 2 || g_conv_impl == 4) && d->Cout < 128), "kd_conv_gemm: the CTA-pair kernel needs Cout >= 128");
+  p.TW = tl.TW; p.TH = tl.TH; p.TB = tl.TB;
+  p.tiles_w = tl.tiles_w; p.tiles_h = tl.tiles_h; p.tiles_b = tl.tiles_b;
   p.chunks_a = d->Ca / BK;
   p.chunks_per_tap = (d->Ca + d->Cb) / BK;
   p.num_kb = taps * p.chunks_per_tap;
   p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out; p.stats = stats; p.logit_w = logit_w; p.logit_parts = logit_parts;
   p.pre_coef = reinterpret_cast<const float2*>(pre_coef);
 
-  // kernel choice: CTA-pair tiles (256 x 256 / 256 x 128) whenever the layer is wide enough, else the single-CTA kernel;
-  // 3x3 convolutions on images of at least 16 x 8 pixels use the halo-reuse variant (impl 4 forces the tap-loop pair kernel)
-  const bool use_pair = (g_conv_impl == 2) || (g_conv_impl == 4) || ((g_conv_impl == 0 || g_conv_impl == 3) && d->Cout >= 128);
-  p.dbg_skip_a = (g_conv_impl == 3) ? 1 : 0;
-  KD_REQUIRE(!((g_conv_impl == 2 || g_conv_impl == 4) && d->Cout < 128), "kd_conv_gemm: the CTA-pair kernel needs Cout >= 128");
-  const bool use_halo = use_pair && g_conv_impl != 4 && g_conv_impl != 3 && d->mode == 0 && d->ksize == 3 && d->H >= HALO_TH &&
-                        d->W >= HALO_TW && !d->out_f32 && d->out_mode == 0;
-  if (use_halo) {  // 16 x 8 pixel tiles, one image per tile
-    p.TW = HALO_TW;
-    p.TH = HALO_TH;
-    p.TB = 1;
-    p.tiles_w = kd_ceil_div(d->W, p.TW);
-    p.tiles_h = kd_ceil_div(d->H, p.TH);
-    p.tiles_b = d->B;
-  }
   const int BN = use_pair ? (d->Cout >= 256 ? 256 : 128) : (d->Cout >= 128 ? 128 : 64);
   p.n_tiles = kd_ceil_div(d->Cout, BN);
   const long long grid = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
