@@ -2,7 +2,7 @@
 (train_ultra_res_v_param.py:27-62, train.py:28-67, train_uncond.py:28-63; defaults per SURVEY.md appendix A.4).
 
 The module owns ordinary ``nn.Parameter``s under the reference's key names (so ``load_state_dict`` of a reference
-checkpoint works); ``forward`` hands them, packed once into TMA-friendly bf16 layouts, to ``UnetExecutor`` which runs
+checkpoint works); ``forward`` hands them, packed once into TMA-friendly fp16 layouts, to ``UnetExecutor`` which runs
 the whole pass with the hand-written CUDA kernels of libkidney_b200.  There is no PyTorch fallback.
 """
 from __future__ import annotations

@@ -3,18 +3,22 @@
 Everything that touches activations is a hand-written kernel reached through ``ops`` (C ABI).  torch is used for
 memory, for one-time weight packing, and for the x-independent nearest resize of the conditioning images.
 
-Data layout in HBM: activations NHWC fp16; "raw" tensors (conv outputs / residual stream) and "act" tensors
-(GroupNorm+SiLU applied, the A operand of the next conv) are both bf16; statistics, softmax, time / conditioning towers
-and the GlobalContext gate are fp32.  Weights are packed once: conv [Cout, kh*kw*Cin] bf16 K-major (tap-major,
-channel-minor) so a (tap, 64-channel chunk) k-block is one TMA box.
+Data layout in HBM: activations NHWC fp16 (saturating conversions); only "raw" tensors (conv outputs / residual stream)
+exist -- the GroupNorm+SiLU'd operand of a 3x3 conv is produced inside the conv kernel; statistics, softmax, time /
+conditioning towers and the GlobalContext gate are fp32.  Weights are packed once: conv [Cout, kh*kw*Cin] fp16 K-major
+(tap-major, channel-minor) so a (tap, 64-channel chunk) k-block is one TMA box.
 
 Fusions relative to the reference's eager graph:
   * channel concat of the up path is never materialised (two TMA sources in the conv kernel; the 2^-0.5 skip scale is
-    applied inside GroupNorm-apply and folded into res_conv's weight columns),
-  * bias / SiLU / GELU / residual add / GlobalContext gate * h + res_conv(x) / pixel-shuffle run in the conv epilogue,
+    folded into the GroupNorm affine and into res_conv's weight columns),
+  * GroupNorm statistics come out of the producing kernel's epilogue (conv / gate_residual), one launch turns them into the
+    per-channel affine {A, B} (incl. the time scale / shift), and the consuming 3x3 conv applies A*x + B and SiLU to its halo
+    tile in shared memory (`_norm_conv`); the separate gn_apply pass remains only for shapes the halo kernel does not take,
+  * bias / SiLU / GELU / residual add / GlobalContext to_k logits / gate * h + res_conv(x) / pixel-shuffle run in the conv
+    epilogue,
   * Downsample's pixel-unshuffle is a 2x2 tap pattern of the TMA loads, Parallel(3x3, 1x1) is one 3x3 conv,
-  * the CrossEmbed init conv is one GEMM (three kernels merged into a 15x15 matrix); its cond-image / low-res part is
-    x-independent and computed once per sample() call,
+  * the CrossEmbed init conv is one panel-free tensor-core kernel (three filters merged into 15x15); its cond-image /
+    low-res part is x-independent and computed once per sample() call,
   * all ResnetBlock time-MLPs are one launch; to_time_cond + to_lowres_time_cond are one launch.
 """
 from __future__ import annotations
@@ -26,16 +30,16 @@ from torch import nn
 from . import ops
 from .modules import Parallel, PixelShuffleUpsample, TransformerBlock, exists
 
-BF16 = ops.ACT_DTYPE  # 16-bit activation / weight dtype (fp16)
+H16 = ops.ACT_DTYPE  # 16-bit activation / weight dtype (saturating fp16)
 IM2COL_BUDGET_BYTES = 4 << 30
 
 
 def _bf(t):
-    return t.detach().to(BF16).contiguous()
+    return t.detach().to(H16).contiguous()
 
 
 def _pack_conv(weight, b_cols=0, b_scale=1.0):
-    """[Cout, Cin, kh, kw] fp32 -> [Cout, kh*kw*Cin] bf16; the last `b_cols` input channels are pre-scaled by b_scale."""
+    """[Cout, Cin, kh, kw] fp32 -> [Cout, kh*kw*Cin] fp16; the last `b_cols` input channels are pre-scaled by b_scale."""
     w = weight.detach().float()
     if w.dim() == 2:
         w = w[:, :, None, None]
@@ -296,7 +300,7 @@ class UnetExecutor:
             assert fixed.shape[1] == self.n_fixed
             S = fixed.shape[-1]
             if "init_base" not in st:
-                st["init_base"] = torch.empty((B, S, S, self.dim), device=fixed.device, dtype=BF16)
+                st["init_base"] = torch.empty((B, S, S, self.dim), device=fixed.device, dtype=H16)
             self.init_base = st["init_base"]
             self._init_gemm(fixed, self.init_wf, self.init_kpf, None, None, self.init_base, getattr(self, "init_df", None))
 
@@ -440,7 +444,7 @@ class UnetExecutor:
             taps["t"], taps["c"] = t, c
 
         # --- init conv (per-step part: the 3 image channels of x; fixed part added in the epilogue)
-        h = torch.empty((B, S, S2, self.dim), device=dev, dtype=BF16)
+        h = torch.empty((B, S, S2, self.dim), device=dev, dtype=H16)
         self._init_gemm(x, self.init_wx, self.init_kpx, self.init_bias, self.init_base, h, getattr(self, "init_dx", None))
         if taps is not None:
             taps["init_conv"] = h

@@ -1,5 +1,5 @@
 """UNet forward + sampler parity: CUDA path (through the C ABI) vs the fp32 CPU oracle on identical random-init weights and
-identical injected noise.  Tolerance from BASELINE.json north_star: rel-L2 <= 1e-2 per step UNet output (bf16 path) and
+identical injected noise.  Tolerance from BASELINE.json north_star: rel-L2 <= 1e-2 per step UNet output (16-bit path; fp16 here) and
 on final samples."""
 import pytest
 import torch
