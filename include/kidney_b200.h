@@ -77,6 +77,9 @@ typedef struct KdConvDesc {
  * CTA-pair (cta_group::2) kernels (halo variant where it applies), 4 = CTA-pair tap-loop kernel only.  All kernels accumulate
  * each output in the same k order: results are bit-identical. */
 int kd_set_conv_impl(int impl);
+/* The library also exports a few `kd_exp_*` symbols (kd_exp_halo_probe: the swizzle / row-offset-descriptor experiment behind
+ * the halo kernel, driven by profiles/halo_probe.py; kd_exp_set_pdl: switches programmatic dependent launch off for A/B
+ * timing).  They are measurement hooks, not part of this ABI, and nothing on the sampling path calls them. */
 
 int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
                  const void* w /* fp16 [Cout, taps*(Ca+Cb)], K ordered (tap, channel) */, const float* bias /* [Cout] or NULL */,
