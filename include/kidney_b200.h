@@ -15,7 +15,7 @@
  * Conventions
  *  - plain pointers + sizes, no torch types; every pointer is DEVICE memory
  *    owned by the caller unless stated otherwise; the library never allocates or
- *    frees device memory and keeps no pointer after return.
+ *    frees device memory (one exception: the kd_peer_* mailbox) and keeps no pointer after return.
  *  - all work is enqueued on `stream` (a cudaStream_t); no implicit device
  *    synchronisation; every call is CUDA-graph capturable.
  *  - return 0 on success, negative KdStatus otherwise; message via
@@ -77,9 +77,6 @@ typedef struct KdConvDesc {
  * CTA-pair (cta_group::2) kernels (halo variant where it applies), 4 = CTA-pair tap-loop kernel only.  All kernels accumulate
  * each output in the same k order: results are bit-identical. */
 int kd_set_conv_impl(int impl);
-/* The library also exports a few `kd_exp_*` symbols (kd_exp_halo_probe: the swizzle / row-offset-descriptor experiment behind
- * the halo kernel, driven by profiles/halo_probe.py; kd_exp_set_pdl: switches programmatic dependent launch off for A/B
- * timing).  They are measurement hooks, not part of this ABI, and nothing on the sampling path calls them. */
 
 int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
                  const void* w /* fp16 [Cout, taps*(Ca+Cb)], K ordered (tap, channel) */, const float* bias /* [Cout] or NULL */,
@@ -244,6 +241,49 @@ int kd_randn(float* out, long n, uint64_t seed, uint64_t key, kd_stream_t stream
 int kd_border_pack(float* inpaint, uint8_t* mask, const float* above, long above_cs, long above_rs, const float* side, long side_cs,
                    long side_rs, const float* corner, long corner_cs, long corner_rs, int S, int overlap_pos, int orientation,
                    kd_stream_t stream);
+
+/* ------------------------------------------------------------------ K9: peer mailbox of the patch-grid sampler (one process per GPU)
+ * replaces: the mp.Manager dict through which generate_image_distributed hands finished patches to other workers
+ *           (sample_ultra_res.py:125-131, 204-205; whole patches pickled through the CPU).  Here a producer copies exactly the
+ *           overlap strip (or previous-stage patch) a dependent on ANOTHER GPU needs into that GPU's mailbox over NVLink (peer
+ *           stores into CUDA-IPC mapped memory) and then raises a flag word there; the consumer's stream waits for the flag on
+ *           the device.  One-sided: no collective, no send/recv matching, no host synchronisation.
+ * The mailbox is the one buffer this library allocates itself (cudaMalloc: IPC export needs a whole allocation): kd_peer_alloc
+ * returns zeroed memory; kd_peer_export writes the 64-byte IPC handle another process passes to kd_peer_open (same node). */
+int kd_peer_alloc(size_t bytes, void** ptr);
+int kd_peer_free(void* ptr);
+int kd_peer_export(const void* ptr, uint8_t* handle /* [64] */);
+int kd_peer_open(const uint8_t* handle /* [64] */, void** ptr);
+int kd_peer_close(void* ptr);
+/* dst[c][y][x] = src[c*cs + y*rs + x] (dst contiguous [C,rows,cols], normally peer memory), then *flag = value with release
+ * semantics at system scope (all strip bytes are visible to a reader that observes the flag). */
+int kd_strip_push(const float* src, long cs, long rs, int C, int rows, int cols, float* dst, uint32_t* flag, uint32_t value,
+                  kd_stream_t stream);
+/* Blocks `stream` (one spinning thread, ld.acquire.sys + nanosleep) until *flag >= value.  timeout_s > 0: gives up after that
+ * many seconds and increments *status (the GPU is never left hanging; the host raises). */
+int kd_flag_wait(const uint32_t* flag, uint32_t value, double timeout_s, uint32_t* status, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ N2: conditioning window of one patch
+ * replaces: the per-patch torch.roll of the WHOLE zoomed image + gap fill + CenterCrop(1024) of get_cond_images
+ *           (sample_ultra_res.py:358-395) by a gather of the P x P window only.  Output position o along an axis reads shifted
+ *           position p = o + off (off = CenterCrop offset; outside [0, W) -> 0, the crop's zero padding); p is fill-coloured when
+ *           shift > 0 ? p < shift : (shift < 0 ? p >= W + shift : true)  [shift == 0 fills everything: reference quirk kept];
+ *           else zoomed[(p - shift) mod W].  channels_out 6 (version v2, :392-395) appends CenterCrop(patch_width) of the window
+ *           (offset center_top) nearest-upsampled to P. */
+int kd_cond_gather(const float* zoomed /* fp32 [3,W,W] */, int W, float* out /* fp32 [channels_out,P,P] */, int channels_out, int P, int off,
+                   int shift_y, int shift_x, float fill, int patch_width, int center_top, kd_stream_t stream);
+
+/* ------------------------------------------------------------------ N3: stitch
+ * replaces: generate_high_res_image's canvas = F.interpolate(zoomed, bilinear) followed by row-major patch pastes where later
+ *           patches overwrite earlier ones (sample_ultra_res.py:440-446; outpainting.py:236-241 with a zero canvas).
+ * cell_index [n*n]: position of grid cell (i, j) in the patch list, -1 when the cell holds no patch.  A canvas pixel belongs to
+ * the covering patch with the LARGEST list index (the survivor of the sequential pastes); kd_patch_paste writes only the pixels
+ * its patch owns and kd_canvas_fill only pixels no patch covers (zoomed == NULL: zeros), so any number of GPUs can paste into
+ * one canvas (peer memory) concurrently and the result equals the sequential loop bit for bit. */
+int kd_canvas_fill(const float* zoomed /* fp32 [3,W,W] or NULL */, int W, float* canvas /* fp32 [3,Wc,Wc] */, int Wc, const int* cell_index,
+                   int n, int patch_dist, int P, kd_stream_t stream);
+int kd_patch_paste(const float* patch /* fp32 [3,P,P] */, float* canvas, int Wc, const int* cell_index, int n, int patch_dist, int P, int k,
+                   int i, int j, kd_stream_t stream);
 
 #ifdef __cplusplus
 }

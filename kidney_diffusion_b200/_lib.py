@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkidney_b200.so")
@@ -78,6 +78,16 @@ SIGNATURES = {
     "kd_q_sample": (c_int, [_P, _P, _F, _F, _P, _L, _P]),
     "kd_randn": (c_int, [_P, _L, c_uint64, c_uint64, _P]),
     "kd_border_pack": (c_int, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _P]),
+    "kd_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "kd_peer_free": (c_int, [_P]),
+    "kd_peer_export": (c_int, [_P, _P]),
+    "kd_peer_open": (c_int, [_P, POINTER(c_void_p)]),
+    "kd_peer_close": (c_int, [_P]),
+    "kd_strip_push": (c_int, [_P, _L, _L, _I, _I, _I, _P, _P, c_uint32, _P]),
+    "kd_flag_wait": (c_int, [_P, c_uint32, c_double, _P, _P]),
+    "kd_cond_gather": (c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P]),
+    "kd_canvas_fill": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "kd_patch_paste": (c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -1,5 +1,6 @@
 // Error plumbing, version and device check for libkidney_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "kd_common.cuh"
 
@@ -12,11 +13,8 @@ void kd_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int g_kd_pdl = 1;
-extern "C" int kd_exp_set_pdl(int on) {
-  g_kd_pdl = on;
-  return 0;
-}
+// programmatic dependent launch between consecutive kernels of a step; KD_NO_PDL=1 in the environment switches it off (A/B timing)
+int g_kd_pdl = getenv("KD_NO_PDL") ? 0 : 1;
 
 int kd_num_sms() {
   static int sms = 0;

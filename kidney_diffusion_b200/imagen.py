@@ -281,7 +281,7 @@ class Imagen(nn.Module):
                post_cond_video_frames=None, inpaint_videos=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5,
                init_images=None, skip_steps=None, batch_size=1, cond_scale=1.0, lowres_sample_noise_level=None,
                start_at_unet_number=1, start_image_or_video=None, stop_at_unet_number=None, return_all_unet_outputs=False,
-               return_pil_images=False, device=None, use_tqdm=True, use_one_unet_in_gpu=True, noise_key=0):
+               return_pil_images=False, device=None, use_tqdm=True, use_one_unet_in_gpu=True, noise_key=None):
         self.eval()
         device = torch.device(default(device, self.device))
         if device.type != "cuda":
@@ -314,7 +314,12 @@ class Imagen(nn.Module):
 
         noise = self.noise_fn
         if noise is None:
-            noise = CounterNoise(self.noise_seed, noise_key)
+            if noise_key is None:
+                # the reference draws from torch's global generator: every call gets fresh noise, reproducible under
+                # torch.manual_seed.  One draw from that generator seeds this call's counter-based streams.
+                noise = CounterNoise(int(torch.randint(0, 2 ** 62, (1,)).item()), 0)
+            else:  # explicit stream key(s) (patch-grid sampler): noise is a pure function of (noise_seed, key, site)
+                noise = CounterNoise(self.noise_seed, noise_key)
         outputs = []
         lowres_sample_noise_level = default(lowres_sample_noise_level, self.lowres_sample_noise_level)
         num_unets = len(self.unets)

@@ -670,3 +670,52 @@ def border_pack(S, overlap_pos, orientation, above, side, corner, device):
     check(lib().kd_border_pack(_ptr(inpaint), _ptr(mask), *args, S, overlap_pos, orientation, _stream()), "kd_border_pack")
     _count()
     return inpaint, mask
+
+
+# ------------------------------------------------------------------------------------------------ K9 peer mailbox / N2 / N3
+def strip_push(view, cs, rs, dst_ptr, flag_ptr, value):
+    """view: fp32 strided strip [C, rows, cols] (element (c,y,x) at c*cs + y*rs + x); dst_ptr / flag_ptr: raw (peer) addresses."""
+    assert view.dtype == torch.float32 and view.is_cuda and view.stride(-1) == 1
+    C, rows, cols = view.shape
+    check(lib().kd_strip_push(_ptr(view), cs, rs, C, rows, cols, ctypes.c_void_p(dst_ptr), ctypes.c_void_p(flag_ptr), value, _stream()),
+          "kd_strip_push")
+    _count(2)
+
+
+def flag_wait(flag_ptr, value, timeout_s, status):
+    check(lib().kd_flag_wait(ctypes.c_void_p(flag_ptr), value, float(timeout_s), _ptr(status), _stream()), "kd_flag_wait")
+    _count()
+
+
+@_timed
+def cond_gather(zoomed, out, off, shift_y, shift_x, fill, patch_width=0, center_top=0):
+    """zoomed: fp32 [3,W,W]; out: fp32 [3|6,P,P] (see kd_cond_gather)."""
+    _chk(zoomed, torch.float32, "zoomed")
+    _chk(out, torch.float32, "out")
+    W, P = zoomed.shape[-1], out.shape[-1]
+    assert zoomed.shape == (3, W, W) and out.shape[0] in (3, 6) and out.shape[1] == P
+    check(lib().kd_cond_gather(_ptr(zoomed), W, _ptr(out), out.shape[0], P, off, shift_y, shift_x, fill, patch_width, center_top, _stream()),
+          "kd_cond_gather")
+    _count()
+    return out
+
+
+@_timed
+def canvas_fill(zoomed, canvas_ptr, Wc, cell_index, n, patch_dist, P):
+    """Background of the stitched canvas (bilinear upsample of `zoomed`, or zeros when None) where no patch covers it."""
+    if zoomed is not None:
+        _chk(zoomed, torch.float32, "zoomed")
+    _chk(cell_index, torch.int32, "cell_index")
+    check(lib().kd_canvas_fill(_ptr(zoomed), 0 if zoomed is None else zoomed.shape[-1], ctypes.c_void_p(canvas_ptr), Wc, _ptr(cell_index), n,
+                               patch_dist, P, _stream()), "kd_canvas_fill")
+    _count()
+
+
+@_timed
+def patch_paste(patch, canvas_ptr, Wc, cell_index, n, patch_dist, k, i, j):
+    _chk(patch, torch.float32, "patch")
+    P = patch.shape[-1]
+    assert patch.numel() == 3 * P * P
+    check(lib().kd_patch_paste(_ptr(patch), ctypes.c_void_p(canvas_ptr), Wc, _ptr(cell_index), n, patch_dist, P, k, i, j, _stream()),
+          "kd_patch_paste")
+    _count()

@@ -31,10 +31,7 @@ def graph_time(fn, reps=50):
     return e0.elapsed_time(e1) / 5 / reps * 1e3  # us per call
 
 
-import ctypes
-_L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kidney_diffusion_b200", "libkidney_b200.so"))
-if os.environ.get("KD_PDL") is not None:
-    _L.kd_exp_set_pdl(int(os.environ["KD_PDL"]))
+# programmatic dependent launch on / off: run with KD_NO_PDL=1 in the environment (read once by libkidney_b200 at load)
 for (B, S, Cin, Cout, k) in ((2, 8, 512, 1024, 1), (2, 8, 1792, 1024, 1), (2, 8, 768, 1024, 3), (2, 16, 768, 768, 3), (2, 32, 256, 256, 3), (2, 64, 512, 256, 3),
                              (16, 8, 768, 1024, 3), (16, 16, 768, 768, 3)):
     x = (torch.randn(B, S, S, Cin, device=dev) * 0.5).half()

@@ -3,9 +3,16 @@ import ctypes, math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-from kidney_diffusion_b200 import _lib
+import subprocess
 
-lib = _lib.load()
+# test-only library: the probe kernel is NOT part of the product libkidney_b200.so
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libkd_experiments.so")
+if not os.path.exists(SO):
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+                           "-I", os.path.join(HERE, "..", "kidney_diffusion_b200", "csrc"), "-o", SO, os.path.join(HERE, "csrc", "kd_experiments.cu"),
+                           os.path.join(HERE, "..", "kidney_diffusion_b200", "csrc", "kd_abi.cu"), "-lcuda"])
+lib = ctypes.CDLL(SO)
 lib.kd_exp_halo_probe.restype = ctypes.c_int
 lib.kd_exp_halo_probe.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                   ctypes.c_int, ctypes.c_void_p]

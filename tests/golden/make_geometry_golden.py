@@ -107,7 +107,28 @@ def mask_rle(mask):
     return out
 
 
+def synthetic_slide(W, seed, dark_background=False):
+    """Slide-like test image: near-neutral background, a few purple tissue blobs, and 3x3 specks the 5x5 erosion must remove."""
+    g = torch.Generator().manual_seed(seed)
+    bg = 0.02 if dark_background else 0.95
+    img = torch.full((1, 3, W, W), bg) + (torch.rand(1, 1, W, W, generator=g) - 0.5) * 0.004
+    yy, xx = torch.meshgrid(torch.arange(W), torch.arange(W), indexing="ij")
+    colour = torch.tensor([0.80, 0.50, 0.80]).view(1, 3, 1, 1)
+    for _ in range(4):
+        cy, cx = (int(v) for v in torch.randint(100, W - 100, (2,), generator=g))
+        ry, rx = (int(v) for v in torch.randint(30, 140, (2,), generator=g))
+        m = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) <= 1.0
+        img = torch.where(m[None, None], colour + (torch.rand(1, 3, W, W, generator=g) - 0.5) * 0.05, img)
+    for _ in range(30):
+        cy, cx = (int(v) for v in torch.randint(2, W - 3, (2,), generator=g))
+        img[:, :, cy - 1:cy + 2, cx - 1:cx + 2] = colour
+    return img.clamp(0, 1).contiguous()
+
+
 def main():
+    import contextlib
+    import io
+
     stub_modules()
     sys.path.insert(0, REF)
     import sample_ultra_res as R
@@ -121,7 +142,8 @@ def main():
     # a13 get_cond_images (mag 1: no tissue filter)
     cond_cases = []
     for version, W, overlap, seed in [("v_param", 1024, 0.25, 1), ("v_param", 1024, 0.5, 2), ("v2", 1024, 0.25, 3), ("airs", 1024, 0.25, 4),
-                                      ("", 700, 0.25, 5), ("v_param", 1190, 0.25, 6), ("v_param", 249, 0.5, 7)]:
+                                      ("", 700, 0.25, 5), ("v_param", 1190, 0.25, 6), ("v_param", 249, 0.5, 7),
+                                      ("v_param", 1158, 0.25, 8)]:  # W=1158: row / column 4 has shift == 0 (the fill-everything quirk of :380-388)
         g = torch.Generator().manual_seed(seed)
         zoomed = torch.rand(1, 3, W, W, generator=g)
         args = Args(version=version, overlap=overlap)
@@ -133,6 +155,22 @@ def main():
         cond_cases.append(dict(version=version, W=W, overlap=overlap, seed=seed, shape=list(cond.shape), n=n, patch_pos=[list(p) for p in pos],
                                sha=sha(cond), first_sha=sha(cond[0]), last_sha=sha(cond[-1])))
     C["cond_images"] = cond_cases
+
+    # a13 at magnification 2: the tissue filter (:317-352).  skimage is absent here, so the reference code runs with OpenCV's
+    # RGB->HSV (an independent implementation; H scaled from degrees to [0,1]) standing in for skimage.color.rgb2hsv.
+    import cv2
+    import numpy as np
+
+    R.color.rgb2hsv = lambda a: cv2.cvtColor(np.ascontiguousarray(a, dtype=np.float32), cv2.COLOR_RGB2HSV) / np.array([360.0, 1.0, 1.0], dtype=np.float32)
+    tissue = []
+    for version, W, seed in [("v_param", 1400, 21), ("airs", 1300, 22)]:
+        zoomed = synthetic_slide(W, seed, dark_background=(version == "airs"))
+        args = Args(version=version, overlap=0.25)
+        with contextlib.redirect_stdout(io.StringIO()):
+            cond, pos, n = R.get_cond_images(args, zoomed.clone(), 2)
+        tissue.append(dict(version=version, W=W, seed=seed, n=n, patch_pos=[list(p) for p in pos], shape=list(cond.shape), sha=sha(cond),
+                           first_sha=sha(cond[0]), last_sha=sha(cond[-1])))
+    C["tissue"] = tissue
 
     # a14 get_next_patches + a15 orientation rule
     nxt = []
