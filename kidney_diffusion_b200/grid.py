@@ -458,6 +458,8 @@ def _messages(plan, patch_pos, orientation, overlap, prev_owner, prev_stage):
 
 
 def _make_plan(patch_pos, orientation, world, stages, args, imagens):
+    """args.cost_table ({stage: {B: ms per step}}, identical on every rank) overrides the built-in cost model; args.plan_policy
+    pins the packing variant; args.max_batch caps the batch (int or {stage: cap})."""
     steps = {}
     for u in stages:
         try:
@@ -468,7 +470,7 @@ def _make_plan(patch_pos, orientation, world, stages, args, imagens):
     n = len(patch_pos)
     mb = {u: max(1, min(mb if isinstance(mb, int) else mb.get(u, MAX_BATCH[u]), n)) for u in (1, 2, 3)}
     return grid_plan.build_plan(patch_pos, orientation, world, stages=stages, steps=steps, resample=max(1, int(args.inpaint_resample)),
-                                max_batch=mb, policy=getattr(args, "plan_policy", None))
+                                max_batch=mb, policy=getattr(args, "plan_policy", None), table=getattr(args, "cost_table", None))
 
 
 def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, orientation, num_patches_width, provider=None):
@@ -508,9 +510,9 @@ def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, 
     transport, plan = None, None
     if world > 1 and device.type == "cuda":
         plan = _make_plan(patch_pos, orientation, world, stages, args, imagens)
-        from .grid_exec import try_peer_mailbox
+        from .grid_exec import cached_peer_mailbox
 
-        transport = try_peer_mailbox(dist, rank, world, device, _messages(plan, patch_pos, orientation, overlap, prev_owner, prev_stage))
+        transport = cached_peer_mailbox(dist, rank, world, device, _messages(plan, patch_pos, orientation, overlap, prev_owner, prev_stage))
         if transport is None:  # NCCL fallback: stage-major, round-synchronous
             prev = lowres_image
             for u in stages:
@@ -592,7 +594,10 @@ def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, 
                     bytes_sent_this_rank=0 if transport is None else transport.bytes_sent, host_wall_s=time.time() - t_wall)
     out.plan = plan
     if transport is not None:
-        transport.close()
+        if hasattr(transport, "recycle"):
+            transport.recycle()  # cached mailbox: barrier + next epoch
+        else:
+            transport.close()
     return out
 
 

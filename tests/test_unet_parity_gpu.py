@@ -254,3 +254,88 @@ def test_text_conditioning_tower_parity(cuda_lib):
         e_t, e_c, e_o = rel_l2(taps_dev["t"], taps_ref["t"]), rel_l2(taps_dev["c"], taps_ref["c"]), rel_l2(out, ref)
         print(f"drop={drop}: t {e_t:.2e} c {e_c:.2e} out {e_o:.2e}")
         assert e_t < 1e-5 and e_c < 1e-5 and e_o < TOL
+
+
+# ------------------------------------------------------------------------------------------------ parity at the benchmarked shape
+FULL_U3 = dict(dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=(2, 4, 6, 8), memory_efficient=True, layer_attns=False,
+               layer_cross_attns=(False, False, False, True), init_conv_to_final_conv_residual=True, cond_images_channels=3)
+
+
+def test_full_width_u3_forward_parity_at_1024(cuda_lib):
+    """The bench shape itself: one forward of the config-3/4 SR UNet on a 1024 x 1024 patch (B = 1) against the fp32 CPU
+    oracle (~12 TFLOP on the host: about a minute).  Covers the TMA boxes / tile scheduler at H = W = 1024."""
+    ou, pu = make_pair(FULL_U3, lowres_cond=True, seed=22)
+    g = torch.Generator().manual_seed(9)
+    S = 1024
+    x, lr, cond = torch.randn(1, 3, S, S, generator=g), torch.randn(1, 3, S, S, generator=g), torch.rand(1, 3, S, S, generator=g)
+    t, lt = torch.tensor([0.9]), torch.tensor([0.7093])
+    with torch.no_grad():
+        ref = ou(x, t, lowres_cond_img=lr, lowres_noise_times=lt, cond_images=cond)
+    ex = pu.executor()
+    ex.set_conditioning(cond_images=cond.cuda(), lowres_cond_img=lr.cuda(), text_embeds=None, text_mask=None, cond_drop_prob=0.0, image_size=S)
+    out = ex.forward(x.cuda(), t.cuda(), lt.cuda())
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    print(f"[full-width u3 @1024, B=1] unet output rel_l2 = {err:.3e}")
+    assert bool(torch.isfinite(out).all()) and err < TOL
+
+
+def test_batch_of_16_at_1024_is_bit_identical_to_single_patches(cuda_lib):
+    """bench.py's B = 16 step works on tensors of exactly 2^31 fp16 elements; every sample of the batch must equal the same
+    patch run alone, bit for bit (the invariance that makes 1/2/4/8-GPU grid runs identical)."""
+    from kidney_diffusion_b200 import Unet
+
+    torch.manual_seed(3)
+    pu = Unet(**FULL_U3, lowres_cond=True, cond_on_text=False, text_embed_dim=None)
+    from kidney_diffusion_b200.factories import randomize_zero_init_
+
+    randomize_zero_init_(pu)
+    pu = pu.cuda().eval()
+    B, S = 16, 1024
+    g = torch.Generator().manual_seed(10)
+    x, lr, cond = torch.randn(B, 3, S, S, generator=g).cuda(), torch.randn(B, 3, S, S, generator=g).cuda(), torch.rand(B, 3, S, S, generator=g).cuda()
+    t, lt = torch.linspace(-3, 5, B).cuda(), torch.full((B,), 0.7093).cuda()
+    ex = pu.executor()
+    ex.set_conditioning(cond_images=cond, lowres_cond_img=lr, text_embeds=None, text_mask=None, cond_drop_prob=0.0, image_size=S)
+    full = ex.forward(x, t, lt).clone()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(full).all())
+    for b in (0, 7, 15):
+        ex.set_conditioning(cond_images=cond[b:b + 1], lowres_cond_img=lr[b:b + 1], text_embeds=None, text_mask=None, cond_drop_prob=0.0, image_size=S)
+        one = ex.forward(x[b:b + 1], t[b:b + 1], lt[b:b + 1])
+        assert torch.equal(one[0], full[b]), f"sample {b} of the batch differs from the single-patch run"
+
+
+def test_consecutive_sample_calls_use_their_own_conditioning(cuda_lib):
+    """Round-1 advisor finding: conditioning tensors built as fresh temporaries (same device address, different contents) must
+    not be mistaken for 'unchanged'."""
+    from kidney_diffusion_b200 import Imagen, NullUnet, Unet
+    from kidney_diffusion_b200.factories import randomize_zero_init_
+
+    torch.manual_seed(4)
+    im = Imagen(unets=(NullUnet(), Unet(**U3_KW)), image_sizes=(16, 64), timesteps=(2, 2), pred_objectives=("noise", "v"),
+                random_crop_sizes=(None, None), condition_on_text=False)
+    randomize_zero_init_(im)
+    im = im.cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    cond = torch.rand(1, 3, 64, 64, generator=g)
+    outs = []
+    for k in range(2):
+        start = torch.rand(1, 3, 16, 16, generator=torch.Generator().manual_seed(50 + k))
+        outs.append(im.sample(batch_size=1, cond_images=cond, start_image_or_video=start.cuda() * 1.0, start_at_unet_number=2, use_tqdm=False,
+                              device="cuda", noise_key=3))
+    fresh = Imagen(unets=(NullUnet(), Unet(**U3_KW)), image_sizes=(16, 64), timesteps=(2, 2), pred_objectives=("noise", "v"),
+                   random_crop_sizes=(None, None), condition_on_text=False)
+    fresh.load_state_dict(im.state_dict())
+    fresh = fresh.cuda().eval()
+    start = torch.rand(1, 3, 16, 16, generator=torch.Generator().manual_seed(51))
+    want = fresh.sample(batch_size=1, cond_images=cond, start_image_or_video=start.cuda(), start_at_unet_number=2, use_tqdm=False, device="cuda", noise_key=3)
+    assert not torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[1], want), "second call sampled against the first call's low-res image"
+    # default noise: fresh per call, reproducible under torch.manual_seed
+    torch.manual_seed(77)
+    a = im.sample(batch_size=1, cond_images=cond, start_image_or_video=start, start_at_unet_number=2, use_tqdm=False, device="cuda")
+    b = im.sample(batch_size=1, cond_images=cond, start_image_or_video=start, start_at_unet_number=2, use_tqdm=False, device="cuda")
+    torch.manual_seed(77)
+    a2 = im.sample(batch_size=1, cond_images=cond, start_image_or_video=start, start_at_unet_number=2, use_tqdm=False, device="cuda")
+    assert not torch.equal(a, b) and torch.equal(a, a2)
