@@ -276,7 +276,7 @@ def grid_section(c, args, steps_box, reduced):
     t0 = time.time()
     table = measure_step_table(c, grid, g_args, sizes)
     t_table = time.time() - t0
-    g_args.cost_table = {u: dict(grid_plan.load_cost_table()[u], **table[u]) for u in (1, 2, 3)}  # measured points override the defaults
+    g_args.cost_table = {u: {**grid_plan.load_cost_table()[u], **table[u]} for u in (1, 2, 3)}  # measured points override the defaults
     plan_full = grid_plan.build_plan(pos, orientation, c.world, steps=full, table=g_args.cost_table)
     g_args.plan_policy = plan_full.policy[0]
     g_args.max_batch = {1: grid.MAX_BATCH[1], 2: grid.MAX_BATCH[2], 3: plan_full.policy[1]}

@@ -74,8 +74,9 @@ typedef struct KdConvDesc {
 } KdConvDesc;
 
 /* Test / profiling hook: 0 = automatic kernel choice (default), 1 = force the single-CTA 128x128 kernel, 2 = force the
- * CTA-pair (cta_group::2) kernels (halo variant where it applies), 4 = CTA-pair tap-loop kernel only.  All kernels accumulate
- * each output in the same k order: results are bit-identical. */
+ * CTA-pair (cta_group::2) kernels (halo variant where it applies), 4 = CTA-pair tap-loop kernel only, 8 = automatic but never
+ * split-K.  Kernels 1 / 2 / 4 accumulate each output in the same k order: their results are bit-identical (split-K adds partial
+ * sums, so it agrees with them to fp32 rounding only). */
 int kd_set_conv_impl(int impl);
 
 int kd_conv_gemm(const KdConvDesc* desc, const void* xa, const void* xb,
@@ -99,7 +100,14 @@ typedef struct KdConvFusion {
   const float* logit_w;
   float* logit_parts;
   const float* pre_coef;
+  void* splitk_ws;        /* caller-owned scratch for shapes that run split-K, >= kd_conv_splitk_workspace_bytes(desc) */
+  size_t splitk_ws_bytes;
 } KdConvFusion;
+/* Convolutions on tiny images (<= 16 x 16 output pixels per sample, K = taps * Cin in the thousands: the 8^2 / 16^2 levels of
+ * the 64^2 base UNet) divide K over several CTAs; a second kernel adds the fp32 partial tiles in fixed split order and applies
+ * the fused epilogue.  The split count depends on the per-sample shape only (never on B), so results stay batch-invariant.
+ * Returns 0 when `desc` does not split (no workspace needed). */
+size_t kd_conv_splitk_workspace_bytes(const KdConvDesc* desc);
 int kd_conv_stats_layout(const KdConvDesc* desc, int* layout /* [4] */);
 int kd_conv_gemm_fused(const KdConvDesc* desc, const void* xa, const void* xb, const void* w, const float* bias, const void* addend,
                        const float* addend_scale, void* out, const KdConvFusion* fusion, kd_stream_t stream);

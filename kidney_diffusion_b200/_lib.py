@@ -25,7 +25,8 @@ class KdConvDesc(Structure):
 
 
 class KdConvFusion(Structure):
-    _fields_ = [("stats", c_void_p), ("logit_w", c_void_p), ("logit_parts", c_void_p), ("pre_coef", c_void_p)]
+    _fields_ = [("stats", c_void_p), ("logit_w", c_void_p), ("logit_parts", c_void_p), ("pre_coef", c_void_p), ("splitk_ws", c_void_p),
+                ("splitk_ws_bytes", c_size_t)]
 
 
 _P = c_void_p
@@ -41,6 +42,7 @@ SIGNATURES = {
     "kd_set_conv_impl": (c_int, [_I]),
     "kd_conv_gemm": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "kd_conv_stats_layout": (c_int, [POINTER(KdConvDesc), POINTER(c_int)]),
+    "kd_conv_splitk_workspace_bytes": (c_size_t, [POINTER(KdConvDesc)]),
     "kd_conv_gemm_fused": (c_int, [POINTER(KdConvDesc), _P, _P, _P, _P, _P, _P, _P, POINTER(KdConvFusion), _P]),
     "kd_linear_small": (c_int, [_P, _I, _I, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
     "kd_sinu_emb": (c_int, [_P, _P, _I, _I, _P, _P]),

@@ -40,10 +40,14 @@ struct ConvParams {
   const float* logit_w;  // optional GlobalContext to_k weight [Cout]: the epilogue also emits per-pixel partial dot products
   float* logit_parts;    // [Cout / 64][B*H*W] fp32, one partial per 64-column group (summed in fixed order by kd_gca_pool)
   const float2* pre_coef;  // optional [B][Ca+Cb] {A, B}: the A operand becomes SiLU(A * x + B) (fused GroupNorm apply, halo kernel)
+  int kb_per_split;        // split-K: k-blocks per split (blockIdx.y selects the split); 0 = the whole K range in one CTA
+  float* splitk_ws;        // split-K: fp32 partial tiles [split][tile][128][BN]
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, int STAGES>
+// SPLIT: the CTA accumulates only k-blocks [blockIdx.y * kb_per_split, ...) and stores its raw fp32 accumulator tile to the
+// split-K workspace; splitk_finish_kernel adds the splits in fixed order and applies the epilogue.
+template <int BN, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
@@ -76,6 +80,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int tile_b = m_tile / p.tiles_h;
   const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, b0 = tile_b * p.TB;
   const int n0 = n_tile * BN;
+  const int kb_lo = SPLIT ? (int)blockIdx.y * p.kb_per_split : 0;
+  const int kb_hi = SPLIT ? min(p.num_kb, kb_lo + p.kb_per_split) : p.num_kb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -107,9 +113,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ================================================================ TMA producer (one elected lane)
     if (lane == 0) {
       const int pad = (p.mode == 0) ? (p.ksize >> 1) : 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const int s = (kb - kb_lo) % STAGES;
+        const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
         mbar_wait_relaxed(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, STAGE_BYTES);
@@ -133,9 +139,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (warp-convergent loop, one elected lane issues)
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      const int s = (kb - kb_lo) % STAGES;
+      const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
       mbar_wait(smem_u32(&full_bar[s]), ph);
       tc_fence_after();
       const uint32_t a_addr = smem_base + s * STAGE_BYTES;
@@ -145,7 +151,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, ((kb - kb_lo) | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot once these MMAs have read it
       }
@@ -173,6 +179,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), acc);
       tmem_ld_wait();
       const int nc = n0 + chunk * 32;
+      if (SPLIT) {  // raw partial tile, every row (rows outside the image hold exact zeros: their A rows were zero-filled)
+        float4* dst = reinterpret_cast<float4*>(p.splitk_ws + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * BM + r) * BN + chunk * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                               __uint_as_float(acc[4 * j + 3]));
+        continue;
+      }
       if (!row_ok || nc >= p.Cout) continue;
 
       long long out_off;   // element offset of column nc for this row
@@ -1146,23 +1160,135 @@ int make_act_map(CUtensorMap* m, const KdConvDesc* d, const void* x, int C, int 
   return encode_map(m, x, 5, dims, str, box);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mw, const ConvParams& p, long long grid,
-           cudaStream_t stream) {
+           cudaStream_t stream, int splits = 1) {
   constexpr int SMEM = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 /*align slack*/ + 128 /*barriers*/ + BN * 4 /*bias*/;
   static bool configured = false;
   static std::mutex mu;
   {
     std::lock_guard<std::mutex> lock(mu);
     if (!configured) {
-      KD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      KD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured = true;
     }
   }
-  KD_CUDA(kd_launch(conv_gemm_kernel<BN, STAGES>, dim3((unsigned)grid), dim3(NUM_THREADS), SMEM, stream, ma, mb, mw, p));
+  KD_CUDA(kd_launch(conv_gemm_kernel<BN, STAGES, SPLIT>, dim3((unsigned)grid, (unsigned)splits), dim3(NUM_THREADS), SMEM, stream, ma, mb, mw, p));
   return KD_OK;
 }
 
+// ---- split-K second pass: out = epilogue(sum over splits, in split order) for one (m-tile, 64-column group) per CTA.
+// warp = 32-row quarter of the tile; lane -> (channel octet o = lane & 7, 8-row slice sl = lane >> 3), the mapping of the fused
+// statistics in pair_epilogue_role: the statistics rows written here have the same geometry as the conv epilogue's.
+__global__ void __launch_bounds__(128) splitk_finish_kernel(const ConvParams p, const int S, const int BN, const int tiles_total) {
+  const int n_g64 = (p.Cout + 63) >> 6;
+  const int g64 = blockIdx.x % n_g64;
+  const int m_lin = blockIdx.x / n_g64;
+  const int n_tile = (g64 * 64) / BN, col0 = (g64 * 64) % BN;
+  const int tile = m_lin * p.n_tiles + n_tile;
+  int m_tile = m_lin;
+  const int tile_w = m_tile % p.tiles_w;
+  m_tile /= p.tiles_w;
+  const int tile_h = m_tile % p.tiles_h;
+  const int tile_b = m_tile / p.tiles_h;
+  const int quarter = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = lane & 7, sl = lane >> 3;
+  const int nc = g64 * 64 + o * 8;
+  const bool col_ok = nc + 8 <= p.Cout;
+  const int Cq = p.Cout >> 2;
+  kd_pdl_wait();
+  kd_pdl_trigger();
+  float bias8[8], lw8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bias8[j] = (p.bias != nullptr && col_ok) ? __ldg(p.bias + nc + j) : 0.f;
+    lw8[j] = (p.logit_w != nullptr && col_ok) ? __ldg(p.logit_w + nc + j) : 0.f;
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < 8; ++i) {
+    const int r = quarter * 32 + sl * 8 + i;
+    const int tw = r % p.TW, th = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
+    const int b = tile_b * p.TB + tb, h = tile_h * p.TH + th, w = tile_w * p.TW + tw;
+    const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const float* src = p.splitk_ws + ((size_t)tile * BM + r) * BN + col0 + o * 8;
+    const size_t split_stride = (size_t)tiles_total * BM * BN;
+    for (int sp = 0; sp < S; ++sp) {  // fixed order: the result does not depend on how many CTAs ran concurrently
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride) + 1);
+      v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += bias8[j];
+    apply_act8(v, p.act);
+    long long out_off = 0;
+    if (row_ok && col_ok) {
+      if (p.out_mode == 1) {
+        const int q4 = nc / Cq, c = nc - q4 * Cq;
+        out_off = (((long long)b * (2 * p.H) + (2 * h + (q4 >> 1))) * (2 * p.W) + (2 * w + (q4 & 1))) * Cq + c;
+      } else {
+        out_off = (((long long)b * p.H + h) * p.W + w) * p.Cout + nc;
+      }
+      if (p.addend != nullptr) {
+        float a[8];
+        if (p.addend_f32) {
+          const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + out_off);
+          const float4 a0 = ap[0], a1 = ap[1];
+          a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        } else {
+          const h16x8 raw = *reinterpret_cast<const h16x8*>(reinterpret_cast<const h16*>(p.addend) + out_off);
+          h16x8_to_float(raw, a);
+        }
+        if (p.addend_scale != nullptr) {
+          const float* gate = p.addend_scale + (long long)b * p.Cout + nc;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] *= __ldg(gate + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    float lacc = 0.f;
+    if (p.out_f32) {
+      if (row_ok && col_ok) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off);
+        op[0] = make_float4(v[0], v[1], v[2], v[3]);
+        op[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      const h16x8 o8 = float_to_h16x8(v);
+      if (row_ok && col_ok) *reinterpret_cast<h16x8*>(reinterpret_cast<h16*>(p.out) + out_off) = o8;
+      float f[8];
+      h16x8_to_float(o8, f);  // statistics / logits of the ROUNDED values, as a pass over the stored tensor would see them
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1 += f[j];
+        s2 = fmaf(f[j], f[j], s2);
+        lacc = fmaf(f[j], lw8[j], lacc);
+      }
+    }
+    if (p.logit_w != nullptr) {  // one partial per (row, 64-column group): merge the 8 octet lanes of the row
+      lacc += __shfl_xor_sync(0xffffffffu, lacc, 1);
+      lacc += __shfl_xor_sync(0xffffffffu, lacc, 2);
+      lacc += __shfl_xor_sync(0xffffffffu, lacc, 4);
+      if (o == 0 && row_ok) p.logit_parts[(long long)g64 * ((long long)p.B * p.H * p.W) + ((long long)b * p.H + h) * p.W + w] = lacc;
+    }
+  }
+  if (p.stats != nullptr) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+    if (sl == 0 && col_ok && tile_b < p.tiles_b)
+      reinterpret_cast<float2*>(p.stats)[((long long)m_lin * 4 + quarter) * (p.Cout >> 3) + (nc >> 3)] = make_float2(s1, s2);
+  }
+}
 
 // output tensor map for the coalesced epilogue (h16 NHWC, or its pixel-shuffle view [B, H, 2(dy), W, 2(dx)*Cq])
 int make_out_map(CUtensorMap* m, const ConvParams& p, void* out) {
@@ -1257,7 +1383,7 @@ int kd_encode_tiled_h16(CUtensorMap* m, const void* base, int rank, const uint64
 }
 
 extern "C" int kd_set_conv_impl(int impl) {
-  if (impl < 0 || impl > 4 || impl == 3) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0, 1, 2 or 4");
+  if (!(impl == 0 || impl == 1 || impl == 2 || impl == 4 || impl == 8)) KD_FAIL(KD_ERR_BAD_ARG, "kd_set_conv_impl: impl must be 0, 1, 2, 4 or 8");
   g_conv_impl = impl;
   return KD_OK;
 }
@@ -1267,10 +1393,38 @@ namespace {
 struct Tiling {
   bool use_pair, use_halo;
   int TW, TH, TB, tiles_w, tiles_h, tiles_b;
+  int splits, kb_per_split, BN;  // split-K (splits > 1): single-CTA 128 x BN tiles, K range divided into `splits` CTAs
 };
+// Split-K applies to convolutions on tiny images (<= 8 x 8 output pixels per sample by default: the 8^2 level of the base UNet),
+// where M = B * H * W gives a handful of tiles while K = 9 * Cin is 7 000 - 18 000: without it one or two CTA pairs walk the
+// whole K range (65 us for 1 GFLOP).  The split count is a function of the PER-SAMPLE shape only -- never of the batch size --
+// so that a sample's accumulation order, hence its bits, does not depend on which other patches share its batch.
+void choose_split(const KdConvDesc* d, Tiling* t) {
+  t->splits = 1;
+  t->kb_per_split = 0;
+  if (g_conv_impl != 0 || d->mode == 2) return;
+  const long hw = (long)d->H * d->W;
+  static int tgt_small = -1, tgt_mid = -1;  // k-blocks per split for <= 8x8 / <= 16x16 images (KD_SPLITK_TARGETS="a,b": tuning hook; 0 = off)
+  if (tgt_small < 0) {
+    int a = 36, b = 0;  // measured on the 64^2 base UNet (profiles/README.md round 2): 36 k-blocks per split at 8x8, no split at 16x16
+    if (const char* e = getenv("KD_SPLITK_TARGETS")) sscanf(e, "%d,%d", &a, &b);
+    tgt_small = a;
+    tgt_mid = b;
+  }
+  const int target = hw <= 64 ? tgt_small : (hw <= 256 ? tgt_mid : 0);
+  if (target == 0) return;
+  const int taps = (d->mode == 1) ? 4 : d->ksize * d->ksize;
+  const int num_kb = taps * ((d->Ca + d->Cb) / BK);
+  int S = num_kb / target;
+  if (S < 2) return;
+  if (S > 32) S = 32;
+  t->kb_per_split = (num_kb + S - 1) / S;
+  t->splits = (num_kb + t->kb_per_split - 1) / t->kb_per_split;
+}
 Tiling choose_tiling(const KdConvDesc* d) {
   Tiling t;
-  t.use_pair = (g_conv_impl == 2) || (g_conv_impl == 4) || (g_conv_impl == 0 && d->Cout >= 128);
+  choose_split(d, &t);
+  t.use_pair = t.splits == 1 && ((g_conv_impl == 2) || (g_conv_impl == 4) || ((g_conv_impl == 0 || g_conv_impl == 8) && d->Cout >= 128));
   t.use_halo = t.use_pair && g_conv_impl != 4 && d->mode == 0 && d->ksize == 3 && d->H >= HALO_TH &&
                d->W >= HALO_TW && !d->out_f32 && d->out_mode == 0;
   if (t.use_halo) {
@@ -1284,6 +1438,7 @@ Tiling choose_tiling(const KdConvDesc* d) {
   t.tiles_w = kd_ceil_div(d->W, t.TW);
   t.tiles_h = kd_ceil_div(d->H, t.TH);
   t.tiles_b = kd_ceil_div(d->B, t.TB);
+  t.BN = t.use_pair ? (d->Cout >= 256 ? 256 : 128) : (d->Cout >= 128 ? 128 : 64);
   return t;
 }
 }  // namespace
@@ -1295,7 +1450,7 @@ extern "C" int kd_conv_stats_layout(const KdConvDesc* d, int* layout) {
   const Tiling t = choose_tiling(d);
   layout[0] = layout[1] = layout[2] = 0;
   layout[3] = t.use_halo ? 1 : 0;
-  if (!t.use_pair || d->out_f32 || d->out_mode != 0 || t.TB > 2 || d->Cout % 8 != 0) return KD_OK;
+  if (!(t.use_pair || t.splits > 1) || d->out_f32 || d->out_mode != 0 || t.TB > 2 || d->Cout % 8 != 0) return KD_OK;
   layout[0] = t.tiles_w * t.tiles_h * t.tiles_b * 4;
   layout[1] = t.tiles_w * t.tiles_h;
   layout[2] = t.TB;
@@ -1305,6 +1460,13 @@ extern "C" int kd_conv_stats_layout(const KdConvDesc* d, int* layout) {
 extern "C" int kd_conv_gemm(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
                             const void* addend, const float* addend_scale, void* out, kd_stream_t stream_) {
   return kd_conv_gemm_fused(d, xa, xb, w, bias, addend, addend_scale, out, nullptr, stream_);
+}
+
+extern "C" size_t kd_conv_splitk_workspace_bytes(const KdConvDesc* d) {
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cout <= 0) return 0;
+  const Tiling t = choose_tiling(d);
+  if (t.splits <= 1) return 0;
+  return (size_t)t.splits * t.tiles_w * t.tiles_h * t.tiles_b * kd_ceil_div(d->Cout, t.BN) * BM * t.BN * sizeof(float);
 }
 
 extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const void* xb, const void* w, const float* bias,
@@ -1346,8 +1508,16 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
   p.bias = bias; p.addend = addend; p.addend_scale = addend_scale; p.out = out; p.stats = stats; p.logit_w = logit_w; p.logit_parts = logit_parts;
   p.pre_coef = reinterpret_cast<const float2*>(pre_coef);
 
-  const int BN = use_pair ? (d->Cout >= 256 ? 256 : 128) : (d->Cout >= 128 ? 128 : 64);
+  const int BN = tl.BN;
   p.n_tiles = kd_ceil_div(d->Cout, BN);
+  p.kb_per_split = tl.splits > 1 ? tl.kb_per_split : 0;
+  p.splitk_ws = nullptr;
+  if (tl.splits > 1) {
+    const size_t need = kd_conv_splitk_workspace_bytes(d);
+    KD_REQUIRE(fusion && fusion->splitk_ws && fusion->splitk_ws_bytes >= need,
+               "kd_conv_gemm: this shape runs split-K and needs a %zu-byte workspace in KdConvFusion (kd_conv_splitk_workspace_bytes)", need);
+    p.splitk_ws = reinterpret_cast<float*>(fusion->splitk_ws);
+  }
   const long long grid = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   KD_REQUIRE(grid > 0 && grid < 2147483647LL, "kd_conv_gemm: grid too large");
 
@@ -1377,6 +1547,13 @@ extern "C" int kd_conv_gemm_fused(const KdConvDesc* d, const void* xa, const voi
     KD_REQUIRE(lay[0] > 0, "kd_conv_gemm_fused: this shape / kernel does not produce fused statistics (see kd_conv_stats_layout)");
     KD_REQUIRE(logit_w == nullptr || (logit_parts != nullptr && addend_scale == nullptr && d->Cout % 64 == 0),
                "kd_conv_gemm_fused: fused GlobalContext logits need Cout %% 64 == 0, an output buffer and no gate");
+  }
+  if (tl.splits > 1) {
+    rc = (BN == 128) ? launch<128, 3, true>(ma, mb, mw, p, grid, stream, tl.splits) : launch<64, 4, true>(ma, mb, mw, p, grid, stream, tl.splits);
+    if (rc) return rc;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    KD_CUDA(kd_launch(splitk_finish_kernel, dim3((unsigned)(m_tiles * ((d->Cout + 63) / 64))), dim3(128), 0, stream, p, tl.splits, BN, (int)grid));
+    return KD_OK;
   }
   const bool tadd = use_pair && addend != nullptr && !d->addend_f32 && !d->out_f32 && d->out_mode == 0;
   if (use_halo) {

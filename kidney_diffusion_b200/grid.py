@@ -745,7 +745,7 @@ def stitch_device(zoomed_image, patches, patch_pos, num_patches_width, overlap, 
         return canvas
     from .grid_exec import try_peer_mailbox
 
-    incoming = {r: [(("canvas",), (3, Wc, Wc))] + [(("done", s), (1,)) for s in range(world) if s != r] for r in range(world)}
+    incoming = {r: [(("canvas",), (3, Wc, Wc))] + [(("done", s), (1, 1, 1)) for s in range(world) if s != r] for r in range(world)}
     box = try_peer_mailbox(dist, rank, world, device, incoming)
     if box is None:  # NCCL fallback: gather on rank 0, stitch there, broadcast
         full = gather_patches(patches)
@@ -766,10 +766,10 @@ def stitch_device(zoomed_image, patches, patch_pos, num_patches_width, overlap, 
                 ops.patch_paste(p, box.base[r] + off[r], Wc, cell, n, patch_dist, k, i, j)
     for r in range(world):
         if r != rank:
-            box.post(r, ("done", rank), token.view(1))
+            box.post(r, ("done", rank), token)
     for s in range(world):
         if s != rank:
-            box.fetch(s, ("done", s), (1,), device)
+            box.fetch(s, ("done", s), (1, 1, 1), device)
     own = box.own[off[rank] // 4: off[rank] // 4 + 3 * Wc * Wc].view(1, 3, Wc, Wc)
     canvas = own.clone()
     box.finish()

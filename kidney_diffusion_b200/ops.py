@@ -99,7 +99,8 @@ def lib():
 
 # ------------------------------------------------------------------------------------------------ K1 conv / GEMM
 def set_conv_impl(impl):
-    """0 = automatic (default), 1 = single-CTA 128x128 kernel, 2 = CTA-pair cta_group::2 kernel (tests / profiling)."""
+    """0 = automatic (default), 1 = single-CTA 128x128 kernel, 2 = CTA-pair cta_group::2 kernel, 4 = pair kernel without halo,
+    8 = automatic without split-K (tests / profiling)."""
     check(lib().kd_set_conv_impl(int(impl)), "kd_set_conv_impl")
 
 
@@ -258,8 +259,10 @@ def conv_gemm(xa, w, bias=None, xb=None, *, mode=0, ksize=3, out_hw=None, act=AC
         if pre_coef is not None:
             _chk(pre_coef, torch.float32, "pre_coef")
             assert pre_coef.shape == (B, Ca + Cb, 2)
+        ws_bytes = lib().kd_conv_splitk_workspace_bytes(ctypes.byref(d))
+        ws = torch.empty((ws_bytes,), device=xa.device, dtype=torch.uint8) if ws_bytes else None
         fz = KdConvFusion(None if stats is None else _ptr(stats.partial), None if logit_parts is None else _ptr(logit_w),
-                          _ptr(logit_parts), _ptr(pre_coef))
+                          _ptr(logit_parts), _ptr(pre_coef), _ptr(ws), ws_bytes)
         check(lib().kd_conv_gemm_fused(ctypes.byref(d), _ptr(xa), _ptr(xb), _ptr(w), _ptr(bias), _ptr(addend), _ptr(addend_scale),
                                        _ptr(out), ctypes.byref(fz), _stream()), "kd_conv_gemm")
     if logit_parts is not None:

@@ -704,3 +704,106 @@ def test_reduce_finalize_single_launch_bit_identical(cuda_lib, B, H, W, Ca, Cb):
     for _ in range(3):
         mr1, cf1 = run(True)
         assert torch.equal(mr0, mr1) and torch.equal(cf0, cf1)
+
+
+# ------------------------------------------------------------------------------------------------ split-K (tiny images, long K)
+SPLITK_CASES = [
+    # B, H, W, Ca, Cb, Cout, k, mode   (the 8^2 / 16^2 levels of the 64^2 base UNet)
+    (1, 8, 8, 1024, 0, 1024, 3, 0),
+    (2, 8, 8, 1024, 768, 1024, 3, 0),     # two sources (up path), tile holds two images
+    (3, 8, 8, 1792, 0, 768, 1, 0),        # 1x1, batch tail inside a tile
+    (2, 4, 8, 1024, 0, 256, 3, 0),        # non-square, tile holds four images -> no fused statistics
+    (2, 8, 8, 512, 0, 512, 2, 1),         # Downsample taps 16x16 -> 8x8
+    (1, 8, 8, 1024, 0, 200, 3, 0),        # Cout not a multiple of 64
+]
+
+
+@pytest.mark.parametrize("B,H,W,Ca,Cb,Cout,k,mode", SPLITK_CASES)
+def test_conv_splitk_matches_conv2d_and_unsplit_kernel(cuda_lib, B, H, W, Ca, Cb, Cout, k, mode):
+    """Split-K path (kd_conv_splitk_workspace_bytes > 0) against F.conv2d and against the un-split kernels (impl 8), with the
+    fused epilogue: bias, SiLU, gated addend, GroupNorm octet statistics, GlobalContext logits."""
+    import ctypes
+
+    from kidney_diffusion_b200 import _lib, ops
+
+    g = torch.Generator().manual_seed(B + H + Ca + Cout)
+    Cin = Ca + Cb
+    Hin, Win = (2 * H, 2 * W) if mode == 1 else (H, W)
+    x = rb(torch.randn(B, Cin, Hin, Win, generator=g))
+    taps = 4 if mode == 1 else k * k
+    w = rb(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * taps))
+    b = torch.randn(Cout, generator=g)
+    add = rb(torch.randn(B, Cout, H, W, generator=g))
+    gate = torch.rand(B, Cout, generator=g)
+    d = _lib.KdConvDesc(mode, B, H, W, Ca, Cb, Cout, k if mode == 0 else 1, ops.ACT_SILU, 0, 0, 0)
+    assert ops.lib().kd_conv_splitk_workspace_bytes(ctypes.byref(d)) > 0, "case must exercise the split-K path"
+    xa = nhwc(x[:, :Ca])
+    xb = nhwc(x[:, Ca:]) if Cb else None
+    if mode == 1:  # Downsample: rearrange 'b c (h 2) (w 2) -> b (c 4) h w' then 1x1 conv; packed weight columns ordered (dy, dx, c)
+        wp = bf(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()).to(DEV)
+        ref = F.conv2d(x, w, b, stride=2)
+    else:
+        wp = pack_w(w)
+        ref = F.conv2d(x, w, b, padding=k // 2)
+    ref = F.silu(ref) + gate[:, :, None, None] * add
+    kw = dict(mode=mode, ksize=k, act=ops.ACT_SILU, addend=nhwc(add), addend_scale=gate.to(DEV), want_stats=True)
+    out = ops.conv_gemm(xa, wp, b.to(DEV), xb=xb, **kw)
+    torch.cuda.synchronize()
+    err = rel_l2(from_nhwc(out), ref)
+    print(f"split-K conv {B}x{H}x{W} {Cin}->{Cout} k{k} mode{mode}: rel_l2={err:.3e}")
+    assert err < 5e-3
+    try:
+        ops.set_conv_impl(8)
+        plain = ops.conv_gemm(xa, wp, b.to(DEV), xb=xb, **kw)
+    finally:
+        ops.set_conv_impl(0)
+    assert rel_l2(out, plain) < 3e-4
+    # fused statistics == statistics of the stored tensor
+    st = getattr(out, "_kd_stats", None)
+    assert st is not None or H * W < 64, "split-K shapes must still emit fused GroupNorm statistics"
+    if st is not None:
+        red = st.reduced().double().sum(1)  # [B, C/8, 2]
+        xo = out.double().reshape(B, H * W, Cout // 8, 8)
+        assert torch.allclose(red[..., 0], xo.sum((1, 3)), rtol=1e-5, atol=1e-3) and torch.allclose(red[..., 1], (xo * xo).sum((1, 3)), rtol=1e-5, atol=1e-3)
+    if Cout % 64 == 0:  # fused GlobalContext logits (no gate allowed on that path)
+        lw = torch.randn(Cout, generator=g).to(DEV)
+        o2 = ops.conv_gemm(xa, wp, b.to(DEV), xb=xb, mode=mode, ksize=k, logit_w=lw)
+        parts = getattr(o2, "_kd_logits", None)
+        assert parts is not None or H * W < 64
+        if parts is not None:
+            want = (o2.float().reshape(B, H * W, Cout) * lw).sum(-1)
+            assert torch.allclose(parts.sum(0), want, rtol=1e-4, atol=1e-3)
+
+
+def test_conv_splitk_is_batch_invariant(cuda_lib):
+    """The split count depends on the per-sample shape only: a sample's result must not change with the batch it is in."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    x = rb(torch.randn(5, 1024, 8, 8, generator=g))
+    w = rb(torch.randn(512, 1024, 3, 3, generator=g) / 96.0)
+    b = torch.randn(512, generator=g).to(DEV)
+    full = ops.conv_gemm(nhwc(x), pack_w(w), b, ksize=3)
+    for i in (0, 3, 4):
+        one = ops.conv_gemm(nhwc(x[i:i + 1]), pack_w(w), b, ksize=3)
+        assert torch.equal(one[0], full[i])
+    pair = ops.conv_gemm(nhwc(x[1:4]), pack_w(w), b, ksize=3)
+    assert torch.equal(pair, full[1:4])
+
+
+def test_conv_splitk_pixel_shuffle_and_f32_out(cuda_lib):
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    B, H, W, Cin, Cout = 2, 8, 8, 1024, 512
+    x = rb(torch.randn(B, Cin, H, W, generator=g))
+    w = rb(torch.randn(Cout, Cin, 1, 1, generator=g) / 32.0)
+    b = torch.randn(Cout, generator=g)
+    y = F.silu(F.conv2d(x, w, b))
+    # PixelShuffleUpsample: weight rows ordered (dy, dx, c) -> out [B, 2H, 2W, Cout/4]
+    co = Cout // 4
+    ref = y.view(B, 4, co, H, W).permute(0, 2, 3, 4, 1).reshape(B, co, H, W, 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, co, 2 * H, 2 * W)
+    out = ops.conv_gemm(nhwc(x), pack_w(w), b.to(DEV), ksize=1, act=ops.ACT_SILU, out_mode=1)
+    assert out.shape == (B, 2 * H, 2 * W, co) and rel_l2(from_nhwc(out), ref) < 5e-3
+    o32 = ops.conv_gemm(nhwc(x), pack_w(w), b.to(DEV), ksize=1, out_f32=True)
+    assert o32.dtype == torch.float32 and rel_l2(from_nhwc(o32), F.conv2d(x, w, b)) < 1e-5
