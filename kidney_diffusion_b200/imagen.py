@@ -13,11 +13,12 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops, schedule
+from . import ops, schedule, torch_ops  # noqa: F401  (torch_ops registers torch.ops.kidney_b200.*)
 from .modules import cast_tuple, default, exists
 from .unet import NullUnet, Unet
 
 SITES = {"lowres_aug": 1, "init": 2, "inpaint": 3, "p_sample": 4, "renoise": 5}
+K = torch.ops.kidney_b200  # the sampler-level kernels are called as PyTorch custom ops (CUDA dispatch key only: no CPU kernel exists)
 
 
 def pad_tuple_to_length(t, length, fillvalue=None):
@@ -144,28 +145,29 @@ class StageRun:
         im, sc, n = self.im, self.scal[step], self.unet_number
         t, t_next = self.times[step]
         if self.has_inpainting:
-            ops.inpaint_blend(self.img, self.inpaint, self.mask_u8, self.noise("inpaint", self.shape, self.device, unet=n, step=step, r=r),
-                              sc["alpha"], sc["sigma"])
+            K.inpaint_blend(self.img, self.inpaint, self.mask_u8, self.noise("inpaint", self.shape, self.device, unet=n, step=step, r=r),
+                            sc["alpha"], sc["sigma"])
         pred = im._unet_step(self.unet, self.img, self.time_table[step], self.lowres_t, self.B, self.S)
         if self.cond_scale != 1.0:  # Unet.forward_with_cond_scale: null + (cond - null) * scale
             null = im._unet_step(self.unet, self.img, self.time_table[step], self.lowres_t, self.B, self.S, drop=1.0)
-            pred = ops.axpby(pred, null, self.cond_scale, 1.0 - self.cond_scale)
+            pred = K.axpby(pred, null, self.cond_scale, 1.0 - self.cond_scale)
         s = None
         if self.dynamic_threshold:
-            s = ops.dynthresh(self.img, pred, self.objective, sc["alpha"], sc["sigma"], im.dynamic_thresholding_percentile, self.ws)
+            s = K.dynthresh(self.img, pred, self.objective, sc["alpha"], sc["sigma"], im.dynamic_thresholding_percentile, self.ws)
         renoise, rn = None, (0.0, 0.0, 1.0)
         if self.has_inpainting and not (r == 0 or bool(t_next == 0)):
             renoise = self.noise("renoise", self.shape, self.device, unet=n, step=step, r=r)
             rn = schedule.renoise_scalars(self.sched, t_next, t)
         x_in = self.img
-        self.img = ops.ddpm_step(x_in, pred, self.noise("p_sample", self.shape, self.device, unet=n, step=step, r=r), s, self.objective, sc,
-                                 renoise=renoise, rn=rn)
+        self.img = K.ddpm_step(x_in, pred, self.noise("p_sample", self.shape, self.device, unet=n, step=step, r=r), s, self.objective,
+                               sc["alpha"], sc["sigma"], sc["one_minus_c"], sc["c"], sc["alpha_next"], sc["std"], renoise, rn[0], rn[1], rn[2])
         if exists(im.step_hook):
             im.step_hook(dict(unet=n, step=step, r=r, x_in=x_in, pred=pred, img=self.img))
         return self.img
 
     def finish(self):
-        img = ops.finalize_image(self.img, self.inpaint if self.has_inpainting else None, self.mask_u8)
+        K.finalize_image(self.img, self.inpaint if self.has_inpainting else None, self.mask_u8)
+        img = self.img
         if not self.im.auto_normalize_img:  # finalize_image un-normalises; undo for the (unused by the reference) raw mode
             img = img * 2 - 1
         return img
@@ -340,8 +342,8 @@ class Imagen(nn.Module):
             if unet.lowres_cond:
                 lowres_cond_img = self.normalize_img(resize_image_to(img, image_size)).contiguous()
                 la, lsig = schedule.alpha_sigma(self.lowres_noise_schedule.noise_schedule, lowres_sample_noise_level)
-                lowres_cond_img = ops.q_sample(lowres_cond_img, noise("lowres_aug", tuple(lowres_cond_img.shape), device, unet=unet_number),
-                                               float(la), float(lsig))
+                lowres_cond_img = K.q_sample(lowres_cond_img, noise("lowres_aug", tuple(lowres_cond_img.shape), device, unet=unet_number),
+                                             float(la), float(lsig))
             shape = (batch_size, self.channels, image_size, image_size)
             img = self.p_sample_loop(
                 unet_number, shape, noise=noise, lowres_cond_img=lowres_cond_img, lowres_noise_level=lowres_sample_noise_level,

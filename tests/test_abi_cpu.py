@@ -63,3 +63,19 @@ def test_no_product_module_imports_the_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("oracle's", ""), fn
+
+
+def test_kernels_are_registered_as_torch_custom_ops_cuda_only():
+    """north_star: "a thin C-ABI layer exposed as PyTorch custom ops".  Every op has a schema in torch.ops.kidney_b200 and a CUDA
+    implementation only: CPU tensors are rejected by the dispatcher (no fallback)."""
+    from kidney_diffusion_b200 import torch_ops
+
+    assert {"conv2d_nhwc", "ddpm_step", "dynthresh", "inpaint_blend", "finalize_image", "q_sample", "border_pack", "attn_mqa", "final_conv",
+            "cond_gather"} <= set(torch_ops.REGISTERED)
+    for name in torch_ops.REGISTERED:
+        op = getattr(torch.ops.kidney_b200, name)
+        assert str(op.default._schema).startswith(f"kidney_b200::{name}(")
+    with pytest.raises(NotImplementedError):
+        torch.ops.kidney_b200.q_sample(torch.zeros(4), torch.zeros(4), 1.0, 0.0)
+    src = open(os.path.join(ROOT, "kidney_diffusion_b200", "imagen.py")).read()
+    assert "torch.ops.kidney_b200" in src and "K.ddpm_step(" in src, "the sampler must call the registered ops"

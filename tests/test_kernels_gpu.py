@@ -807,3 +807,25 @@ def test_conv_splitk_pixel_shuffle_and_f32_out(cuda_lib):
     assert out.shape == (B, 2 * H, 2 * W, co) and rel_l2(from_nhwc(out), ref) < 5e-3
     o32 = ops.conv_gemm(nhwc(x), pack_w(w), b.to(DEV), ksize=1, out_f32=True)
     assert o32.dtype == torch.float32 and rel_l2(from_nhwc(o32), F.conv2d(x, w, b)) < 1e-5
+
+
+def test_torch_custom_ops_match_direct_wrappers(cuda_lib):
+    """torch.ops.kidney_b200.* (the registered custom ops) launch the same kernels as the ctypes wrappers."""
+    from kidney_diffusion_b200 import ops, torch_ops  # noqa: F401
+
+    K = torch.ops.kidney_b200
+    g = torch.Generator().manual_seed(0)
+    x, pred, noise = (torch.randn(2, 3, 32, 32, generator=g).to(DEV) for _ in range(3))
+    sc = dict(alpha=0.8, sigma=0.6, one_minus_c=0.9, c=0.1, alpha_next=0.85, std=0.05)
+    s = K.dynthresh(x, pred, "v", sc["alpha"], sc["sigma"], 0.95, None)
+    assert torch.equal(s, ops.dynthresh(x, pred, "v", sc["alpha"], sc["sigma"], 0.95))
+    a = K.ddpm_step(x, pred, noise, s, "v", sc["alpha"], sc["sigma"], sc["one_minus_c"], sc["c"], sc["alpha_next"], sc["std"], None, 0.0, 0.0, 1.0)
+    assert torch.equal(a, ops.ddpm_step(x, pred, noise, s, "v", sc))
+    xa = bf(torch.randn(1, 16, 16, 64, generator=g)).to(DEV)
+    w = bf(torch.randn(128, 576, generator=g) / 24).to(DEV)
+    assert torch.equal(K.conv2d_nhwc(xa, w, None, None, 0, 3, 0, 0, False, None, None), ops.conv_gemm(xa, w, None, ksize=3))
+    patch = torch.rand(3, 64, 64, generator=g).to(DEV)
+    ip, m = K.border_pack(64, 16, -1, patch[:, 48:, :], patch[:, :, 48:], None, patch)
+    ip2, m2 = ops.border_pack(64, 16, -1, *ops.neighbour_strips(64, 16, -1, above=patch, side=patch)[:2], None, patch.device)
+    assert torch.equal(ip, ip2) and torch.equal(m, m2)
+    assert torch.equal(K.randn_like(x, 5, 9), ops.randn(tuple(x.shape), 5, 9, x.device))

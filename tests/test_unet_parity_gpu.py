@@ -339,3 +339,54 @@ def test_consecutive_sample_calls_use_their_own_conditioning(cuda_lib):
     torch.manual_seed(77)
     a2 = im.sample(batch_size=1, cond_images=cond, start_image_or_video=start, start_at_unet_number=2, use_tqdm=False, device="cuda")
     assert not torch.equal(a, b) and torch.equal(a, a2)
+
+
+# ------------------------------------------------------------------------------------------------ a16: trainer chunking + generate_images wrappers
+def _tiny_uncond(unet_number):
+    from kidney_diffusion_b200 import Imagen, Unet
+    from kidney_diffusion_b200.factories import FixedNullUnet, randomize_zero_init_
+
+    torch.manual_seed(40 + unet_number)
+    kws = {1: U1_KW, 2: dict(U2_KW, cond_images_channels=0), 3: dict(U3_KW, cond_images_channels=0)}
+    unets = tuple(Unet(**kws[n]) if n == unet_number else FixedNullUnet(lowres_cond=n > 1) for n in (1, 2, 3))
+    im = Imagen(unets=unets, image_sizes=(16, 32, 64), timesteps=(3, 2, 2), pred_objectives=("noise", "noise", "noise"),
+                random_crop_sizes=(None, None, None), condition_on_text=False)
+    randomize_zero_init_(im)
+    return im.cuda().eval()
+
+
+def test_trainer_sample_max_batch_size_chunks(cuda_lib):
+    """ImagenTrainer.sample(max_batch_size=...) == the same chunks sampled one by one (sample_uncond.py:37-55 loop)."""
+    from kidney_diffusion_b200 import ImagenTrainer
+
+    im = _tiny_uncond(1)
+    tr = ImagenTrainer(imagen=im)
+    torch.manual_seed(5)
+    whole = tr.sample(batch_size=5, max_batch_size=2, stop_at_unet_number=1, use_tqdm=False)
+    torch.manual_seed(5)
+    parts = [im.sample(batch_size=n, stop_at_unet_number=1, use_tqdm=False, device="cuda") for n in (2, 2, 1)]
+    assert whole.shape == (5, 3, 16, 16) and torch.equal(whole, torch.cat(parts, 0))
+    assert not torch.equal(whole[:2], whole[2:4]), "chunks must draw fresh noise"
+
+
+def test_generate_images_wrappers(cuda_lib, tmp_path):
+    """samplers.generate_images_uncond (sample_uncond.py:21-74): per-stage checkpoint load, chunked sampling, CPU hand-off, PNG
+    output of the last stage."""
+    import types
+
+    from kidney_diffusion_b200 import samplers
+
+    paths = {}
+    for n in (1, 2, 3):
+        paths[n] = tmp_path / f"u{n}.pt"
+        torch.save(dict(model=_tiny_uncond(n).state_dict(), version="1.18.5"), paths[n])
+    out_dir = tmp_path / "out"
+    out_dir.mkdir()
+    args = types.SimpleNamespace(unet1_checkpoint=str(paths[1]), unet2_checkpoint=str(paths[2]), unet3_checkpoint=str(paths[3]), num_images=3,
+                                 folder_name=str(out_dir))
+    low = samplers.generate_images_uncond(1, args, init_imagen=_tiny_uncond, batch_sizes=[2, 2, 2])
+    assert low.shape == (3, 3, 16, 16) and not low.is_cuda
+    med = samplers.generate_images_uncond(2, args, lowres_images=low, init_imagen=_tiny_uncond, batch_sizes=[2, 2, 2])
+    assert med.shape == (3, 3, 32, 32)
+    assert samplers.generate_images_uncond(3, args, lowres_images=med, init_imagen=_tiny_uncond, batch_sizes=[2, 2, 2]) is None
+    assert len(list(out_dir.glob("inference-*.png"))) == 3
