@@ -711,9 +711,9 @@ SPLITK_CASES = [
     # B, H, W, Ca, Cb, Cout, k, mode   (the 8^2 / 16^2 levels of the 64^2 base UNet)
     (1, 8, 8, 1024, 0, 1024, 3, 0),
     (2, 8, 8, 1024, 768, 1024, 3, 0),     # two sources (up path), tile holds two images
-    (3, 8, 8, 1792, 0, 768, 1, 0),        # 1x1, batch tail inside a tile
+    (3, 8, 8, 4608, 0, 768, 1, 0),        # 1x1, batch tail inside a tile
     (2, 4, 8, 1024, 0, 256, 3, 0),        # non-square, tile holds four images -> no fused statistics
-    (2, 8, 8, 512, 0, 512, 2, 1),         # Downsample taps 16x16 -> 8x8
+    (2, 8, 8, 1152, 0, 512, 2, 1),        # Downsample taps 16x16 -> 8x8
     (1, 8, 8, 1024, 0, 200, 3, 0),        # Cout not a multiple of 64
 ]
 
