@@ -293,6 +293,12 @@ int kd_canvas_fill(const float* zoomed /* fp32 [3,W,W] or NULL */, int W, float*
 int kd_patch_paste(const float* patch /* fp32 [3,P,P] */, float* canvas, int Wc, const int* cell_index, int n, int patch_dist, int P, int k,
                    int i, int j, kd_stream_t stream);
 
+/* ------------------------------------------------------------------ overflow guard of the fp16 activation path
+ * The reference runs fp32; this path stores UNet activations as fp16 with saturating conversions (+-65504).  Adds to *counter the
+ * number of elements of the fp16 tensor x[n] whose magnitude is >= 65504 (clipped values) or that are not finite.  Debug aid:
+ * Imagen.check_saturation runs it on every stored activation tensor of a sample() call. */
+int kd_count_saturated(const void* x, long n, unsigned long long* counter, kd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

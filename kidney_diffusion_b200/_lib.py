@@ -80,6 +80,7 @@ SIGNATURES = {
     "kd_q_sample": (c_int, [_P, _P, _F, _F, _P, _L, _P]),
     "kd_randn": (c_int, [_P, _L, c_uint64, c_uint64, _P]),
     "kd_border_pack": (c_int, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _P]),
+    "kd_count_saturated": (c_int, [_P, _L, _P, _P]),
     "kd_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "kd_peer_free": (c_int, [_P]),
     "kd_peer_export": (c_int, [_P, _P]),

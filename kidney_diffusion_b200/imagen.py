@@ -225,6 +225,10 @@ class Imagen(nn.Module):
         self._graphs = {}
         self._pools = {}
         self.step_hook = None  # optional callable(dict) per inner iteration (parity taps)
+        # overflow guard of the fp16 activation path: when True, sample() runs without CUDA graphs, counts every stored activation
+        # value that was clipped at +-65504 (kd_count_saturated) and leaves the total in `last_saturation_count`
+        self.check_saturation = False
+        self.last_saturation_count = None
 
     @property
     def device(self):
@@ -314,6 +318,27 @@ class Imagen(nn.Module):
             f"invalid text embedding dimension being passed in (should be {self.text_embed_dim})")
         assert not (exists(inpaint_images) ^ exists(inpaint_masks)), "inpaint images and masks must be both passed in to do inpainting"
 
+        guard = None
+        if self.check_saturation:
+            guard = dict(graph=self.use_cuda_graph, counter=torch.zeros(1, dtype=torch.int64, device=device))
+            self.use_cuda_graph, ops.sat_counter = False, guard["counter"]
+        try:
+            return self._sample(device, texts, text_masks, text_embeds, cond_images, inpaint_videos, inpaint_images, inpaint_masks,
+                                inpaint_resample_times, batch_size, cond_scale, lowres_sample_noise_level, start_at_unet_number,
+                                start_image_or_video, stop_at_unet_number, return_all_unet_outputs, return_pil_images, noise_key)
+        finally:
+            if guard is not None:
+                ops.sat_counter, self.use_cuda_graph = None, guard["graph"]
+                self.last_saturation_count = int(guard["counter"].item())
+                if self.last_saturation_count:
+                    import warnings
+
+                    warnings.warn(f"{self.last_saturation_count} activation values were clipped at the fp16 range (+-65504) during sample(): "
+                                  "these weights overflow the 16-bit activation path")
+
+    def _sample(self, device, texts, text_masks, text_embeds, cond_images, inpaint_videos, inpaint_images, inpaint_masks, inpaint_resample_times,
+                batch_size, cond_scale, lowres_sample_noise_level, start_at_unet_number, start_image_or_video, stop_at_unet_number,
+                return_all_unet_outputs, return_pil_images, noise_key):
         noise = self.noise_fn
         if noise is None:
             if noise_key is None:

@@ -22,6 +22,7 @@ conv_profile = None  # bench.py sets this to a list: every tensor-core GEMM laun
 
 
 op_profile = None  # bench / profiling: list of (op name, start_event, end_event, tensor bytes in + out) for EVERY op when set
+sat_counter = None  # overflow guard: int64 device tensor [1]; while set, every op that stores an fp16 activation tensor counts clipped values
 
 
 def _timed(fn):
@@ -30,6 +31,12 @@ def _timed(fn):
 
     @functools.wraps(fn)
     def wrapper(*a, **k):
+        if sat_counter is not None:
+            out = fn(*a, **k)
+            for t in (out if isinstance(out, (tuple, list)) else [out]):
+                if isinstance(t, torch.Tensor) and t.dtype == ACT_DTYPE and t.is_cuda and t.is_contiguous() and t.numel():
+                    check(lib().kd_count_saturated(_ptr(t), t.numel(), _ptr(sat_counter), _stream()), "kd_count_saturated")
+            return out
         if op_profile is None:
             return fn(*a, **k)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

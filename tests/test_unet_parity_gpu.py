@@ -390,3 +390,57 @@ def test_generate_images_wrappers(cuda_lib, tmp_path):
     assert med.shape == (3, 3, 32, 32)
     assert samplers.generate_images_uncond(3, args, lowres_images=med, init_imagen=_tiny_uncond, batch_sizes=[2, 2, 2]) is None
     assert len(list(out_dir.glob("inference-*.png"))) == 3
+
+
+# ------------------------------------------------------------------------------------------------ fp16 range: large-magnitude residual stream
+def _scaled_pair(scale):
+    ou, pu = make_pair(U3_KW, lowres_cond=True, seed=77)
+    with torch.no_grad():
+        for m in (ou, pu):
+            for conv in m.init_conv.convs:
+                conv.weight.mul_(scale)
+                conv.bias.mul_(scale)
+    return ou, pu
+
+
+def test_large_magnitude_residual_stream_and_saturation_guard(cuda_lib):
+    """imagen-pytorch's architecture is known to produce large activations on trained weights.  (a) a residual stream of ~1e4
+    (init conv scaled) stays inside fp16's range: nothing is clipped and the UNet output still matches the fp32 oracle; (b) a
+    stream beyond 65504 is clipped by the saturating conversions -- never inf / NaN -- and Imagen.check_saturation reports it."""
+    from kidney_diffusion_b200 import Imagen, NullUnet, ops
+
+    g = torch.Generator().manual_seed(5)
+    S = 64
+    x, lr, cond = torch.randn(1, 3, S, S, generator=g), torch.randn(1, 3, S, S, generator=g), torch.rand(1, 3, S, S, generator=g)
+    t, lt = torch.tensor([1.0]), torch.tensor([0.7093])
+    for scale, expect_clip in ((3e3, False), (1e5, True)):
+        ou, pu = _scaled_pair(scale)
+        taps = {}
+        with torch.no_grad():
+            ref = ou(x, t, lowres_cond_img=lr, lowres_noise_times=lt, cond_images=cond, taps=taps)
+        stream = float(taps["init_conv"].abs().max())
+        counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ops.sat_counter = counter
+        try:
+            ex = pu.executor()
+            ex.set_conditioning(cond_images=cond.cuda(), lowres_cond_img=lr.cuda(), text_embeds=None, text_mask=None, cond_drop_prob=0.0, image_size=S)
+            out = ex.forward(x.cuda(), t.cuda(), lt.cuda())
+            torch.cuda.synchronize()
+        finally:
+            ops.sat_counter = None
+        clipped = int(counter.item())
+        err = rel_l2(out, ref)
+        print(f"init-conv scale {scale:g}: residual stream max |h| = {stream:.3g}, clipped values = {clipped}, rel_l2 vs fp32 oracle = {err:.3e}")
+        assert bool(torch.isfinite(out).all()), "saturating conversions must keep the output finite"
+        if expect_clip:
+            assert stream > 65504 and clipped > 0
+        else:
+            assert 1e4 <= stream < 65504 and clipped == 0 and err < TOL
+    # the same guard through the public API
+    torch.manual_seed(1)
+    im = Imagen(unets=(NullUnet(), _scaled_pair(1e5)[1]), image_sizes=(16, 64), timesteps=(2, 2), pred_objectives=("noise", "v"),
+                random_crop_sizes=(None, None), condition_on_text=False).cuda().eval()
+    im.check_saturation = True
+    with pytest.warns(UserWarning, match="clipped at the fp16 range"):
+        res = im.sample(batch_size=1, cond_images=cond, start_image_or_video=torch.rand(1, 3, 16, 16), start_at_unet_number=2, use_tqdm=False, device="cuda")
+    assert im.last_saturation_count > 0 and bool(torch.isfinite(res).all())
