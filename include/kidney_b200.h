@@ -171,6 +171,11 @@ int kd_rowdot(const void* x /* fp16 [B,HW,C] */, const float* w /* [C] */, const
 int kd_gca_pool(const void* x, const float* logits /* [n_parts][B*HW]: partial logits, summed per pixel */, int n_parts, int B, long HW,
                 int C, int nblk, float* part /* [B][nblk][C] */, float* ml /* [B][nblk][2] = {max, sumexp} */, kd_stream_t stream);
 int kd_gca_finalize(const float* part, const float* ml, int B, int nblk, int C, float* pooled /* [B][C] */, kd_stream_t stream);
+/* kd_gca_finalize + GlobalContext.net (Conv1x1 C -> hid, SiLU, Conv1x1 hid -> C, Sigmoid) in ONE launch: a cluster of 8 CTAs per
+ * image merges the pooling partials, splits both matrix-vector products by output rows and passes the hidden vector through
+ * distributed shared memory.  gate[b][c] is what kd_gate_residual / the residual conv's epilogue multiplies h by. */
+int kd_gca_gate(const float* part, const float* ml, int B, int nblk, int C, int hid, const float* w0 /* [hid][C] */, const float* b0,
+                const float* w1 /* [C][hid] */, const float* b1, float* gate /* [B][C] */, kd_stream_t stream);
 /* out = h * gate[b,c] + res   (gate NULL -> 1, res NULL -> 0); fp16 in/out.  oct_partial (optional, [B][nblk][C/8][2]):
  * fused statistics of `out` in kd_oct_stats form, nblk = kd_elementwise_blocks(HW, C). */
 int kd_gate_residual(const void* h, const float* gate, const void* res, void* out, float* oct_partial, int B, long HW, int C,

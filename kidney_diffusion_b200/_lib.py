@@ -53,6 +53,7 @@ SIGNATURES = {
     "kd_rowdot": (c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
     "kd_gca_pool": (c_int, [_P, _P, _I, _I, _L, _I, _I, _P, _P, _P]),
     "kd_gca_finalize": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "kd_gca_gate": (c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "kd_gate_residual": (c_int, [_P, _P, _P, _P, _P, _I, _L, _I, _P]),
     "kd_elementwise_blocks": (c_int, [_L, _I]),
     "kd_oct_stats": (c_int, [_P, _I, _L, _I, _P, _I, _P]),

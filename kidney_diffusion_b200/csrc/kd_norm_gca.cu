@@ -775,6 +775,120 @@ int pick_nblk(long HW, int lanes, int B) {
   return (int)want;
 }
 
+// ---- GlobalContext tail in ONE launch: softmax-pool finalize -> Conv1x1(C -> hid) + SiLU -> Conv1x1(hid -> C) + sigmoid.
+// One cluster of GG_CL CTAs per batch image.  Every CTA merges the pooling partials (cheap, redundant); the two matrix-vector
+// products are split by output rows over the cluster's CTAs (the weights, up to 2 x 2 MB fp32 at C = 1024, are streamed once per
+// image by 8 SMs instead of by one); the hidden vector travels between the CTAs through distributed shared memory.
+// Replaces kd_gca_finalize + 2 x kd_linear_small (three dependent ~5 us launches per ResnetBlock; 42 blocks per 1024^2 step).
+constexpr int GG_CL = 8;
+__device__ __forceinline__ void gg_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(GG_CL, 1, 1) __launch_bounds__(256)
+gca_gate_kernel(const float* __restrict__ part, const float* __restrict__ ml, int nblk, int C, int hid, const float* __restrict__ w0,
+                const float* __restrict__ b0, const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ gate) {
+  extern __shared__ float gsm[];  // pooled[C] | hidden_full[hid] | hidden_local[hp] | f[nblk]
+  __shared__ float s_red[8];
+  __shared__ float s_M, s_L;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int b = blockIdx.x / GG_CL;
+  const int hp = (hid + GG_CL - 1) / GG_CL, cp = (C + GG_CL - 1) / GG_CL;
+  float* pooled = gsm;
+  float* hidden_full = pooled + C;
+  float* hidden_local = hidden_full + hid;
+  float* f = hidden_local + hp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  kd_pdl_wait();
+  kd_pdl_trigger();
+  // ---- phase 1: merge the online-softmax partials of kd_gca_pool (fixed order)
+  const float* mlb = ml + (long)b * nblk * 2;
+  float m = -INFINITY;
+  for (int k = threadIdx.x; k < nblk; k += 256) m = fmaxf(m, mlb[k * 2]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = -INFINITY;
+    for (int i = 0; i < 8; ++i) mm = fmaxf(mm, s_red[i]);
+    s_M = mm;
+  }
+  __syncthreads();
+  const float M = s_M;
+  float l = 0.f;
+  for (int k = threadIdx.x; k < nblk; k += 256) {
+    const float mk = mlb[k * 2];
+    const float fk = (mk == -INFINITY) ? 0.f : __expf(mk - M);
+    f[k] = fk;
+    l += fk * mlb[k * 2 + 1];
+  }
+  l = warp_sum(l);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ll = 0.f;
+    for (int i = 0; i < 8; ++i) ll += s_red[i];
+    s_L = ll;
+  }
+  __syncthreads();
+  const float inv_L = 1.0f / s_L;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float* pp = part + (long)b * nblk * C + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 3 < nblk; k += 4) {
+      s0 = fmaf(pp[(long)k * C], f[k], s0);
+      s1 = fmaf(pp[(long)(k + 1) * C], f[k + 1], s1);
+      s2 = fmaf(pp[(long)(k + 2) * C], f[k + 2], s2);
+      s3 = fmaf(pp[(long)(k + 3) * C], f[k + 3], s3);
+    }
+    for (; k < nblk; ++k) s0 = fmaf(pp[(long)k * C], f[k], s0);
+    pooled[c] = ((s0 + s1) + (s2 + s3)) * inv_L;
+  }
+  __syncthreads();
+  // ---- phase 2: this CTA's rows of the hidden layer
+  const int j0 = (int)rank * hp, j1 = min(hid, j0 + hp);
+  for (int j = j0 + warp; j < j1; j += 8) {
+    const float* wr = w0 + (long)j * C;
+    float acc = 0.f;
+    for (int k = lane * 4; k < C; k += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+      const float4 xv = *reinterpret_cast<const float4*>(pooled + k);
+      acc += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) hidden_local[j - j0] = silu_f(acc + b0[j]);
+  }
+  gg_cluster_sync();
+  // ---- phase 3: gather the whole hidden vector through distributed shared memory
+  for (int idx = threadIdx.x; idx < hid; idx += 256) {
+    const uint32_t r = (uint32_t)(idx / hp);
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(remote)
+                 : "r"((uint32_t)__cvta_generic_to_shared(hidden_local + (idx - (int)r * hp))), "r"(r));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    hidden_full[idx] = v;
+  }
+  gg_cluster_sync();  // nobody leaves (or reuses smem) while a peer still reads its hidden_local
+  // ---- phase 4: this CTA's channels of the gate
+  const int c0 = (int)rank * cp, c1 = min(C, c0 + cp);
+  for (int c = c0 + warp; c < c1; c += 8) {
+    const float* wr = w1 + (long)c * hid;
+    float acc = 0.f;
+    for (int k = lane * 4; k < hid; k += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+      const float4 xv = *reinterpret_cast<const float4*>(hidden_full + k);
+      acc += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) gate[(long)b * C + c] = sigmoid_f(acc + b1[c]);
+  }
+}
+
 }  // namespace
 
 #define KD_CHECK_OCT(C)                                                                                   \
@@ -843,6 +957,17 @@ extern "C" int kd_gca_pool(const void* x, const float* logits, int n_parts, int 
   const size_t smem = sizeof(float) * (size_t)T * 8;
   gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const h16*>(x), logits, n_parts, (long)B * HW, HW, C, nblk, part, ml);
   KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_gca_gate(const float* part, const float* ml, int B, int nblk, int C, int hid, const float* w0, const float* b0,
+                           const float* w1, const float* b1, float* gate, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(part && ml && w0 && b0 && w1 && b1 && gate && B > 0 && nblk > 0 && nblk <= 8192, "kd_gca_gate: bad argument");
+  KD_REQUIRE(C > 0 && C % 4 == 0 && hid > 0 && hid % 4 == 0, "kd_gca_gate: C (%d) and hid (%d) must be multiples of 4", C, hid);
+  const size_t smem = sizeof(float) * ((size_t)C + hid + (hid + GG_CL - 1) / GG_CL + nblk + 8);
+  KD_REQUIRE(smem <= 48 * 1024, "kd_gca_gate: shape too large for shared memory");
+  KD_CUDA(kd_launch(gca_gate_kernel, dim3(B * GG_CL), dim3(256), smem, stream, part, ml, nblk, C, hid, w0, b0, w1, b1, gate));
   return KD_OK;
 }
 

@@ -416,6 +416,32 @@ def gca_pool(x, logits):
     return pooled
 
 
+FUSED_GCA_GATE = True  # debugging switch: False runs kd_gca_finalize + two kd_linear_small launches instead of kd_gca_gate
+
+
+@_timed
+def gca_gate(x, logits, w0, b0, w1, b1):
+    """GlobalContext gate [B, C] of NHWC fp16 `x`: softmax-pool over pixels (kd_gca_pool) then finalize + MLP + sigmoid in one
+    cluster launch (kd_gca_gate)."""
+    B, H, W, C = x.shape
+    HW = H * W
+    hid = w0.shape[0]
+    nblk = _nblk(HW, C, B)
+    if not (FUSED_GCA_GATE and C % 4 == 0 and hid % 4 == 0 and 4 * (C + hid + hid // 8 + 16 + nblk) <= 48 * 1024):
+        pooled = gca_pool(x, logits)
+        return linear_small(linear_small(pooled, w0, b0, post_act=ACT_SILU), w1, b1, post_act=ACT_SIGMOID)
+    n_parts = logits.shape[0] if logits.dim() == 3 else 1
+    part = torch.empty((B, nblk, C), device=x.device, dtype=torch.float32)
+    ml = torch.empty((B, nblk, 2), device=x.device, dtype=torch.float32)
+    check(lib().kd_gca_pool(_ptr(x), _ptr(logits), n_parts, B, HW, C, nblk, _ptr(part), _ptr(ml), _stream()), "kd_gca_pool")
+    gate = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    for t, name in ((w0, "w0"), (b0, "b0"), (w1, "w1"), (b1, "b1")):
+        _chk(t, torch.float32, name)
+    check(lib().kd_gca_gate(_ptr(part), _ptr(ml), B, nblk, C, hid, _ptr(w0), _ptr(b0), _ptr(w1), _ptr(b1), _ptr(gate), _stream()), "kd_gca_gate")
+    _count(2)
+    return gate
+
+
 @_timed
 def gate_residual(h, gate, res, want_stats=False):
     _chk(h, ACT_DTYPE, "h")

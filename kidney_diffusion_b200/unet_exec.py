@@ -373,9 +373,7 @@ class UnetExecutor:
             logits = getattr(h2, "_kd_logits", None)  # to_k from the conv epilogue (its bias cancels in the softmax)
             if logits is None:
                 logits = ops.rowdot(h2, g["wk"], g["bk"])
-            pooled = ops.gca_pool(h2, logits)
-            hid = ops.linear_small(pooled, g["w0"], g["b0"], post_act=ops.ACT_SILU)
-            gate = ops.linear_small(hid, g["w1"], g["b1"], post_act=ops.ACT_SIGMOID)
+            gate = ops.gca_gate(h2, logits, g["w0"], g["b0"], g["w1"], g["b1"])
             if exists(P.wr):  # out = res_conv(x) + gate * h2, fused in the 1x1 conv epilogue
                 return ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1, addend=h2, addend_scale=gate, want_stats=True)
             return ops.gate_residual(h2, gate, xa, want_stats=True)

@@ -259,6 +259,13 @@ def test_global_context_gate_residual(cuda_lib, B, H, W, C):
     hid = ops.linear_small(pooled, gca.net[0].weight.detach().view(-1, C).to(DEV), gca.net[0].bias.detach().to(DEV), post_act=ops.ACT_SILU)
     gate = ops.linear_small(hid, gca.net[2].weight.detach().view(C, -1).to(DEV), gca.net[2].bias.detach().to(DEV), post_act=ops.ACT_SIGMOID)
     e_gate = rel_l2(gate, gate_ref.view(B, C))
+    # the same tail as ONE cluster launch (kd_gca_gate: finalize + MLP + sigmoid), what the executor runs
+    w0, b0 = gca.net[0].weight.detach().view(-1, C).to(DEV).contiguous(), gca.net[0].bias.detach().to(DEV)
+    w1, b1 = gca.net[2].weight.detach().view(C, -1).to(DEV).contiguous(), gca.net[2].bias.detach().to(DEV)
+    fused = ops.gca_gate(dx, logits, w0, b0, w1, b1)
+    assert rel_l2(fused, gate_ref.view(B, C)) < 1e-4 and rel_l2(fused, gate) < 1e-5
+    if B > 1:  # batch invariance: one cluster per image
+        assert torch.equal(ops.gca_gate(dx[1:2].contiguous(), logits[1:2].contiguous(), w0, b0, w1, b1)[0], fused[1])
     out = ops.gate_residual(dx, gate, nhwc(res))
     err = rel_l2(from_nhwc(out), ref)
     print("gca gate rel_l2", e_gate, "out", err)
