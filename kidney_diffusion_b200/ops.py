@@ -416,7 +416,7 @@ def gca_pool(x, logits):
     return pooled
 
 
-FUSED_GCA_GATE = True  # debugging switch: False runs kd_gca_finalize + two kd_linear_small launches instead of kd_gca_gate
+FUSED_GCA_GATE = False  # opt-in: kd_gca_gate (finalize + MLP + sigmoid as one 8-CTA cluster launch) instead of kd_gca_finalize + two kd_linear_small; measured neutral at B = 16 (193.0 vs 194.9 ms) and 3 % slower at B = 1 (8 CTAs stream the MLP weights instead of 64-128), see profiles/README.md
 
 
 @_timed
