@@ -199,6 +199,23 @@ int kd_attn_mqa(const void* q /* fp16 [B,N,*] */, long ldq, const void* kv /* fp
 int kd_attn_cross(const void* q, long ldq, const float* kv /* [B,Jc,2*heads*64] */, const float* null_kv /* [2,64] */,
                   void* out /* fp16 [B,N,heads*64] */, int B, int N, int Jc, int heads, float scale, kd_stream_t stream);
 
+/* ------------------------------------------------------------------ linear attention (Unet(use_linear_attn=...), north_star (b))
+ * replaces: imagen_pytorch.LinearAttention.forward after the 1x1 convolutions (which run on kd_conv_gemm):
+ *   kd_dwconv3x3      : the depthwise 3x3 convolutions of to_q / to_k / to_v (groups = channels, no bias) on the concatenated
+ *                       q|k|v map, NHWC fp16; w fp32 [C][3][3];
+ *   kd_linattn_context: k <- softmax over positions (N pixels of columns [k_col, k_col+heads*64) of `qkv` plus J fp32 context-token
+ *                       rows ctx_kv [B][J][2*heads*64] = k | v), ctx[b][h][d][e] = sum_n k[n,h,d] v[n,h,e] (fp32 [B][heads][64][64]);
+ *                       pixel chunks are reduced in fixed order (chunk count = kd_linattn_blocks(N), independent of B);
+ *   kd_linattn_apply  : out[n, h*64+e] = act(scale * sum_d softmax_d(q[n,h,:])[d] * ctx[h][d][e]), fp16 [B][N][heads*64].
+ * The products are 64 x 64 per head (no tensor-core tile fits); the block is bound by one pass over q, k and v. */
+int kd_dwconv3x3(const void* x, const float* w, void* y, int B, int H, int W, int C, kd_stream_t stream);
+int kd_linattn_blocks(int N);
+size_t kd_linattn_workspace_bytes(int B, int N, int heads);
+int kd_linattn_context(const void* qkv, long ld, int k_col, int v_col, int B, int N, int heads, const float* ctx_kv, int J, float* workspace,
+                       size_t ws_bytes, float* ctx, kd_stream_t stream);
+int kd_linattn_apply(const void* q, long ld, int q_col, const float* ctx, void* out, int B, int N, int heads, float scale, int act,
+                     kd_stream_t stream);
+
 /* replaces: PerceiverAttention of the text-conditioning tower (Unet.attn_pool; train.py models only): fp32 multi-head
  *           attention of Nq latent queries over J keys, q [B,Nq,heads*64], kv [B,J,2*heads*64] (k | v), once per sample(). */
 int kd_attn_small_f32(const float* q, const float* kv, float* out, int B, int Nq, int J, int heads, float scale, kd_stream_t stream);

@@ -82,6 +82,11 @@ SIGNATURES = {
     "kd_randn": (c_int, [_P, _L, c_uint64, c_uint64, _P]),
     "kd_border_pack": (c_int, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _P]),
     "kd_count_saturated": (c_int, [_P, _L, _P, _P]),
+    "kd_dwconv3x3": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "kd_linattn_blocks": (c_int, [_I]),
+    "kd_linattn_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "kd_linattn_context": (c_int, [_P, _L, _I, _I, _I, _I, _I, _P, _I, _P, c_size_t, _P, _P]),
+    "kd_linattn_apply": (c_int, [_P, _L, _I, _P, _P, _I, _I, _I, _F, _I, _P]),
     "kd_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "kd_peer_free": (c_int, [_P]),
     "kd_peer_export": (c_int, [_P, _P]),

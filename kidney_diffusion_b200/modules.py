@@ -168,6 +168,34 @@ class TransformerBlock(_NoCall):
         )
 
 
+class LinearAttention(_NoCall):
+    """imagen-pytorch LinearAttention: to_q / to_k / to_v = Sequential(Dropout, Conv2d 1x1, depthwise Conv2d 3x3), no biases."""
+
+    def __init__(self, dim, dim_head=32, heads=8, dropout=0.05, context_dim=None, **kwargs):
+        super().__init__()
+        self.scale, self.heads, self.dim_head = dim_head ** -0.5, heads, dim_head
+        inner = dim_head * heads
+        self.norm = GainLayerNorm(dim, dim=-3)
+        self.nonlin = nn.SiLU()
+
+        def qkv():
+            return nn.Sequential(nn.Dropout(dropout), nn.Conv2d(dim, inner, 1, bias=False),
+                                 nn.Conv2d(inner, inner, 3, bias=False, padding=1, groups=inner))
+
+        self.to_q, self.to_k, self.to_v = qkv(), qkv(), qkv()
+        self.to_context = nn.Sequential(nn.LayerNorm(context_dim), nn.Linear(context_dim, inner * 2, bias=False)) if exists(context_dim) else None
+        self.to_out = nn.Sequential(nn.Conv2d(inner, dim, 1, bias=False), GainLayerNorm(dim, dim=-3))
+
+
+class LinearAttentionTransformerBlock(_NoCall):
+    def __init__(self, dim, *, depth=1, heads=8, dim_head=32, ff_mult=2, context_dim=None, **kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList(
+            [nn.ModuleList([LinearAttention(dim=dim, heads=heads, dim_head=dim_head, context_dim=context_dim), ChanFeedForward(dim=dim, mult=ff_mult)])
+             for _ in range(depth)]
+        )
+
+
 class ResnetBlock(_NoCall):
     def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, use_gca=False, **attn_kwargs):
         super().__init__()

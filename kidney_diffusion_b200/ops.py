@@ -529,6 +529,43 @@ def attn_small_f32(q, kv, heads, scale):
 
 
 @_timed
+def dwconv3x3(x, w):
+    """Depthwise 3x3 convolution (zero padding, no bias): x NHWC fp16 [B,H,W,C], w fp32 [C,3,3]."""
+    _chk(x, ACT_DTYPE, "x")
+    _chk(w, torch.float32, "w")
+    B, H, W, C = x.shape
+    assert w.shape == (C, 3, 3)
+    y = torch.empty_like(x)
+    check(lib().kd_dwconv3x3(_ptr(x), _ptr(w), _ptr(y), B, H, W, C, _stream()), "kd_dwconv3x3")
+    _count()
+    return y
+
+
+@_timed
+def linear_attention(qkv, heads, scale, ctx_kv=None, act=ACT_SILU):
+    """qkv: fp16 [B, N, 3*heads*64] (q | k | v after the depthwise convs); ctx_kv: fp32 [B, J, 2*heads*64] (k | v of the context
+    tokens) or None -> fp16 [B, N, heads*64] = act(scale * softmax_d(q) @ (softmax_n(k)^T v))."""
+    _chk(qkv, ACT_DTYPE, "qkv")
+    B, N, ld = qkv.shape
+    inner = heads * 64
+    assert ld == 3 * inner
+    J = 0
+    if ctx_kv is not None:
+        _chk(ctx_kv, torch.float32, "ctx_kv")
+        J = ctx_kv.shape[1]
+        assert ctx_kv.shape == (B, J, 2 * inner)
+    nbytes = lib().kd_linattn_workspace_bytes(B, N, heads)
+    ws = torch.empty((nbytes,), device=qkv.device, dtype=torch.uint8)
+    ctx = torch.empty((B, heads, 64, 64), device=qkv.device, dtype=torch.float32)
+    check(lib().kd_linattn_context(_ptr(qkv), ld, inner, 2 * inner, B, N, heads, _ptr(ctx_kv), J, _ptr(ws), nbytes, _ptr(ctx), _stream()),
+          "kd_linattn_context")
+    out = torch.empty((B, N, inner), device=qkv.device, dtype=ACT_DTYPE)
+    check(lib().kd_linattn_apply(_ptr(qkv), ld, 0, _ptr(ctx), _ptr(out), B, N, heads, scale, act, _stream()), "kd_linattn_apply")
+    _count(4)
+    return out
+
+
+@_timed
 def axpby(x, y, a, b):
     _chk(x, torch.float32, "x")
     _chk(y, torch.float32, "y")

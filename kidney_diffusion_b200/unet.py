@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from .modules import (
-    CrossEmbedLayer, Downsample, LearnedSinusoidalPosEmb, Parallel, PerceiverResampler, PixelShuffleUpsample, ResnetBlock,
+    CrossEmbedLayer, Downsample, LearnedSinusoidalPosEmb, LinearAttentionTransformerBlock, Parallel, PerceiverResampler, PixelShuffleUpsample, ResnetBlock,
     TransformerBlock, cast_tuple, default, exists,
 )
 
@@ -32,7 +32,7 @@ class Unet(nn.Module):
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
         unsupported = dict(
-            use_linear_attn=use_linear_attn, use_linear_cross_attn=use_linear_cross_attn, cross_embed_downsample=cross_embed_downsample,
+            use_linear_cross_attn=use_linear_cross_attn, cross_embed_downsample=cross_embed_downsample,
             self_cond=self_cond, combine_upsample_fmaps=combine_upsample_fmaps,
         )
         for k, v in unsupported.items():
@@ -107,10 +107,11 @@ class Unet(nn.Module):
 
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
-        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns]
+        use_linear_attn = cast_tuple(use_linear_attn, num_layers)
+        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns, use_linear_attn]
         reversed_layer_params = [tuple(reversed(p)) for p in layer_params]
         skip_connect_dims = []
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn) in enumerate(zip(in_out, *layer_params)):
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(zip(in_out, *layer_params)):
             is_last = ind >= (num_layers - 1)
             layer_cond_dim = cond_dim if layer_cross_attn else None
             current_dim = dim_in
@@ -135,7 +136,8 @@ class Unet(nn.Module):
                              for _ in range(n_blocks)]
                         ),
                         TransformerBlock(dim=current_dim, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
-                        if layer_attn else nn.Identity(),
+                        if layer_attn else (LinearAttentionTransformerBlock(dim=current_dim, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
+                                            if layer_lin else nn.Identity()),
                         post_downsample,
                     ]
                 )
@@ -144,7 +146,7 @@ class Unet(nn.Module):
         self.mid_block1 = ResnetBlock(mid_dim, mid_dim, cond_dim=cond_dim, time_cond_dim=time_cond_dim, groups=resnet_groups[-1], **attn_kwargs)
         self.mid_attn = TransformerBlock(mid_dim, depth=layer_mid_attns_depth, **attn_kwargs) if attend_at_middle else None
         self.mid_block2 = ResnetBlock(mid_dim, mid_dim, cond_dim=cond_dim, time_cond_dim=time_cond_dim, groups=resnet_groups[-1], **attn_kwargs)
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn) in enumerate(
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(
             zip(reversed(in_out), *reversed_layer_params)
         ):
             is_last = ind == (len(in_out) - 1)
@@ -159,7 +161,8 @@ class Unet(nn.Module):
                              for _ in range(n_blocks)]
                         ),
                         TransformerBlock(dim=dim_out, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
-                        if layer_attn else nn.Identity(),
+                        if layer_attn else (LinearAttentionTransformerBlock(dim=dim_out, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
+                                            if layer_lin else nn.Identity()),
                         PixelShuffleUpsample(dim_out, dim_in) if not is_last or memory_efficient else nn.Identity(),
                     ]
                 )

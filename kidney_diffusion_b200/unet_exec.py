@@ -28,7 +28,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .modules import Parallel, PixelShuffleUpsample, TransformerBlock, exists
+from .modules import LinearAttentionTransformerBlock, Parallel, PixelShuffleUpsample, TransformerBlock, exists
 
 H16 = ops.ACT_DTYPE  # 16-bit activation / weight dtype (saturating fp16)
 IM2COL_BUDGET_BYTES = 4 << 30
@@ -102,6 +102,35 @@ class _Xf:
                 d["ctx"] = dict(ln_w=a.to_context[0].weight.detach(), ln_b=a.to_context[0].bias.detach(),
                                 w=a.to_context[1].weight.detach(), b=a.to_context[1].bias.detach())
             self.layers.append(d)
+
+
+class _LinXf:
+    """Packed LinearAttentionTransformerBlock: the three 1x1 convolutions of to_q / to_k / to_v become one GEMM with 3 * inner output
+    channels, their depthwise 3x3 convolutions one depthwise pass over the concatenated map."""
+
+    def __init__(self, m):
+        self.layers = []
+        for a, ff in m.layers:
+            assert a.dim_head == 64, "linear-attention kernels are built for dim_head = 64"
+            d = dict(
+                heads=a.heads, scale=a.scale, norm_g=a.norm.g.detach().reshape(-1).contiguous(),
+                wqkv1=_pack_conv(torch.cat([t[1].weight.detach() for t in (a.to_q, a.to_k, a.to_v)], 0)),
+                wdw=torch.cat([t[2].weight.detach() for t in (a.to_q, a.to_k, a.to_v)], 0).reshape(-1, 3, 3).float().contiguous(),
+                wo=_pack_conv(a.to_out[0].weight), out_g=a.to_out[1].g.detach().reshape(-1).contiguous(), ctx=None,
+                ff_g0=ff[0].g.detach().reshape(-1).contiguous(), ff_w1=_pack_conv(ff[1].weight),
+                ff_g1=ff[3].g.detach().reshape(-1).contiguous(), ff_w2=_pack_conv(ff[4].weight),
+            )
+            if exists(a.to_context):
+                d["ctx"] = dict(ln_w=a.to_context[0].weight.detach(), ln_b=a.to_context[0].bias.detach(), w=a.to_context[1].weight.detach())
+            self.layers.append(d)
+
+
+def _pack_attn(m):
+    if isinstance(m, TransformerBlock):
+        return _Xf(m)
+    if isinstance(m, LinearAttentionTransformerBlock):
+        return _LinXf(m)
+    return None
 
 
 class UnetExecutor:
@@ -197,7 +226,7 @@ class UnetExecutor:
                 d["pre"] = self._pack_down(pre[1])
             d["init"] = res(init_block)
             d["blocks"] = [res(b) for b in blocks]
-            d["attn"] = _Xf(attn) if isinstance(attn, TransformerBlock) else None
+            d["attn"] = _pack_attn(attn)
             if exists(post):
                 if isinstance(post, Parallel):
                     c3, c1 = post.fns
@@ -214,7 +243,7 @@ class UnetExecutor:
         for init_block, blocks, attn, up in u.ups:
             skip_c = init_block.dim - init_block.dim_out
             d = dict(init=res(init_block, skip_c, s), blocks=[res(b, b.dim - b.dim_out, s) for b in blocks],
-                     attn=_Xf(attn) if isinstance(attn, TransformerBlock) else None, up=None)
+                     attn=_pack_attn(attn), up=None)
             if isinstance(up, PixelShuffleUpsample):
                 conv = up.net[0]
                 co4, ci = conv.weight.shape[0], conv.weight.shape[1]
@@ -382,7 +411,30 @@ class UnetExecutor:
             return self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, addend=r, want_stats=True)
         return self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, addend=xa, want_stats=True)
 
+    def _lin_transformer(self, P, x, c):
+        """LinearAttentionTransformerBlock.forward: x = attn(x, context) + x; x = ff(x) + x."""
+        B, H, W, C = x.shape
+        N = H * W
+        for L in P.layers:
+            xn = ops.layernorm_h16(x, L["norm_g"])
+            qkv = ops.dwconv3x3(ops.conv_gemm(xn, L["wqkv1"], None, ksize=1), L["wdw"]).view(B, N, -1)
+            ctx_kv = None
+            if exists(c) and exists(L["ctx"]):
+                J = c.shape[1]
+                cn = ops.layernorm_f32(c.view(B * J, -1), L["ctx"]["ln_w"], L["ctx"]["ln_b"])
+                ctx_kv = ops.linear_small(cn, L["ctx"]["w"], None).view(B, J, -1)
+            o = ops.linear_attention(qkv, L["heads"], L["scale"], ctx_kv)
+            o = ops.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
+            x = ops.layernorm_h16(o, L["out_g"], residual=x)
+            f = ops.layernorm_h16(x, L["ff_g0"])
+            f = ops.conv_gemm(f, L["ff_w1"], None, ksize=1, act=ops.ACT_GELU)
+            f = ops.layernorm_h16(f, L["ff_g1"])
+            x = ops.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
+        return x
+
     def _transformer(self, P, x, c):
+        if isinstance(P, _LinXf):
+            return self._lin_transformer(P, x, c)
         B, H, W, C = x.shape
         N = H * W
         for L in P.layers:

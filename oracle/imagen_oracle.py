@@ -403,6 +403,64 @@ class TransformerBlock(nn.Module):
         return x
 
 
+class LinearAttention(nn.Module):
+    """imagen_pytorch.LinearAttention (1.18.x): q / k / v = 1x1 conv + depthwise 3x3 conv of the channel-normalised map; softmax of
+    q over the head dimension and of k over positions (pixels + optional context tokens), context = k^T v, out = q context,
+    SiLU, 1x1 conv + ChanLayerNorm.  Dropout(0.05) of the to_q / to_k / to_v stacks is inactive at sampling time."""
+
+    def __init__(self, dim, dim_head=32, heads=8, dropout=0.05, context_dim=None, **kwargs):
+        super().__init__()
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        inner_dim = dim_head * heads
+        self.norm = ChanLayerNorm(dim)
+        self.nonlin = nn.SiLU()
+
+        def qkv():
+            return nn.Sequential(nn.Dropout(dropout), nn.Conv2d(dim, inner_dim, 1, bias=False),
+                                 nn.Conv2d(inner_dim, inner_dim, 3, bias=False, padding=1, groups=inner_dim))
+
+        self.to_q, self.to_k, self.to_v = qkv(), qkv(), qkv()
+        self.to_context = nn.Sequential(nn.LayerNorm(context_dim), nn.Linear(context_dim, inner_dim * 2, bias=False)) if exists(context_dim) else None
+        self.to_out = nn.Sequential(nn.Conv2d(inner_dim, dim, 1, bias=False), ChanLayerNorm(dim))
+
+    def forward(self, fmap, context=None):
+        h, x, y = self.heads, *fmap.shape[-2:]
+        b = fmap.shape[0]
+        fmap = self.norm(fmap)
+        q, k, v = (fn(fmap) for fn in (self.to_q, self.to_k, self.to_v))
+        q, k, v = (t.reshape(b, h, -1, x * y).transpose(-1, -2).reshape(b * h, x * y, -1) for t in (q, k, v))  # 'b (h c) x y -> (b h) (x y) c'
+        if exists(context):
+            assert exists(self.to_context)
+            ck, cv = self.to_context(context).chunk(2, dim=-1)
+            ck, cv = (t.reshape(b, t.shape[1], h, -1).transpose(1, 2).reshape(b * h, t.shape[1], -1) for t in (ck, cv))  # 'b n (h d) -> (b h) n d'
+            k = torch.cat((k, ck), dim=-2)
+            v = torch.cat((v, cv), dim=-2)
+        q = q.softmax(dim=-1)
+        k = k.softmax(dim=-2)
+        q = q * self.scale
+        context = torch.einsum("b n d, b n e -> b d e", k, v)
+        out = torch.einsum("b n d, b d e -> b n e", q, context)
+        out = out.reshape(b, h, x, y, -1).permute(0, 1, 4, 2, 3).reshape(b, -1, x, y)  # '(b h) (x y) d -> b (h d) x y'
+        out = self.nonlin(out)
+        return self.to_out(out)
+
+
+class LinearAttentionTransformerBlock(nn.Module):
+    def __init__(self, dim, *, depth=1, heads=8, dim_head=32, ff_mult=2, context_dim=None, **kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([LinearAttention(dim=dim, heads=heads, dim_head=dim_head, context_dim=context_dim),
+                                              ChanFeedForward(dim=dim, mult=ff_mult)]))
+
+    def forward(self, x, context=None):
+        for attn, ff in self.layers:
+            x = attn(x, context=context) + x
+            x = ff(x) + x
+        return x
+
+
 class ResnetBlock(nn.Module):
     def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, use_gca=False, **attn_kwargs):
         super().__init__()
@@ -525,6 +583,7 @@ class Unet(nn.Module):
         init_dim=None, resnet_groups=8, init_cross_embed_kernel_sizes=(3, 7, 15), attn_pool_text=True,
         attn_pool_num_latents=32, memory_efficient=False, init_conv_to_final_conv_residual=False,
         use_global_context_attn=True, scale_skip_connection=True, final_resnet_block=True, final_conv_kernel_size=3,
+        use_linear_attn=False,
     ):
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
@@ -588,11 +647,12 @@ class Unet(nn.Module):
 
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
-        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns]
+        use_linear_attn = cast_tuple(use_linear_attn, num_layers)
+        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns, use_linear_attn]
         reversed_layer_params = [tuple(reversed(p)) for p in layer_params]
         skip_connect_dims = []
 
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn) in enumerate(zip(in_out, *layer_params)):
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(zip(in_out, *layer_params)):
             is_last = ind >= (num_layers - 1)
             layer_cond_dim = cond_dim if layer_cross_attn else None
             current_dim = dim_in
@@ -617,7 +677,8 @@ class Unet(nn.Module):
                              for _ in range(n_blocks)]
                         ),
                         TransformerBlock(dim=current_dim, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
-                        if layer_attn else Identity(),
+                        if layer_attn else (LinearAttentionTransformerBlock(dim=current_dim, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
+                                            if layer_lin else Identity()),
                         post_downsample,
                     ]
                 )
@@ -628,7 +689,7 @@ class Unet(nn.Module):
         self.mid_attn = TransformerBlock(mid_dim, depth=layer_mid_attns_depth, **attn_kwargs) if attend_at_middle else None
         self.mid_block2 = ResnetBlock(mid_dim, mid_dim, cond_dim=cond_dim, time_cond_dim=time_cond_dim, groups=resnet_groups[-1], **attn_kwargs)
 
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn) in enumerate(
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(
             zip(reversed(in_out), *reversed_layer_params)
         ):
             is_last = ind == (len(in_out) - 1)
@@ -643,7 +704,8 @@ class Unet(nn.Module):
                              for _ in range(n_blocks)]
                         ),
                         TransformerBlock(dim=dim_out, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
-                        if layer_attn else Identity(),
+                        if layer_attn else (LinearAttentionTransformerBlock(dim=dim_out, depth=attn_depth, ff_mult=ff_mult, context_dim=cond_dim, **attn_kwargs)
+                                            if layer_lin else Identity()),
                         PixelShuffleUpsample(dim_out, dim_in) if not is_last or memory_efficient else Identity(),
                     ]
                 )

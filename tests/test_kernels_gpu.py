@@ -836,3 +836,49 @@ def test_torch_custom_ops_match_direct_wrappers(cuda_lib):
     ip2, m2 = ops.border_pack(64, 16, -1, *ops.neighbour_strips(64, 16, -1, above=patch, side=patch)[:2], None, patch.device)
     assert torch.equal(ip, ip2) and torch.equal(m, m2)
     assert torch.equal(K.randn_like(x, 5, 9), ops.randn(tuple(x.shape), 5, 9, x.device))
+
+
+# ------------------------------------------------------------------------------------------------ linear attention (north_star b)
+@pytest.mark.parametrize("B,H,W,dim,Jc", [(2, 16, 16, 128, 0), (1, 32, 32, 256, 6), (3, 20, 12, 64, 3)])
+def test_linear_attention_block_matches_oracle(cuda_lib, B, H, W, dim, Jc):
+    """LinearAttention.forward of the oracle (fp32 CPU) against the CUDA pipeline the executor runs: ChanLayerNorm -> fused q|k|v
+    1x1 conv -> depthwise 3x3 -> kd_linattn_context / kd_linattn_apply -> 1x1 conv -> ChanLayerNorm."""
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import LinearAttention
+
+    torch.manual_seed(dim + H)
+    cd = 96
+    mod = LinearAttention(dim, dim_head=64, heads=8, context_dim=cd if Jc else None).eval()
+    with torch.no_grad():
+        for t in (mod.to_q, mod.to_k, mod.to_v):
+            t[1].weight.copy_(rb(t[1].weight * 2.0))
+            t[2].weight.mul_(2.0)
+        mod.to_out[0].weight.copy_(rb(mod.to_out[0].weight))
+        mod.norm.g.copy_(torch.rand_like(mod.norm.g) + 0.5)
+    x = rb(torch.randn(B, dim, H, W))
+    ctx = torch.randn(B, Jc, cd) if Jc else None
+    with torch.no_grad():
+        ref = mod(x, context=ctx)
+    dx = nhwc(x)
+    xn = ops.layernorm_h16(dx, mod.norm.g.detach().reshape(-1).to(DEV))
+    w1 = pack_w(torch.cat([t[1].weight.detach() for t in (mod.to_q, mod.to_k, mod.to_v)], 0))
+    wdw = torch.cat([t[2].weight.detach() for t in (mod.to_q, mod.to_k, mod.to_v)], 0).reshape(-1, 3, 3).contiguous().to(DEV)
+    qkv1 = ops.conv_gemm(xn, w1, None, ksize=1)
+    qkv = ops.dwconv3x3(qkv1, wdw)
+    # depthwise conv alone vs F.conv2d on the same (fp16-rounded) input
+    want_dw = F.conv2d(from_nhwc(qkv1), wdw.cpu().reshape(-1, 1, 3, 3), padding=1, groups=wdw.shape[0])
+    assert rel_l2(from_nhwc(qkv), want_dw) < 1e-3
+    ckv = None
+    if Jc:
+        cn = ops.layernorm_f32(ctx.to(DEV).view(B * Jc, cd), mod.to_context[0].weight.detach().to(DEV), mod.to_context[0].bias.detach().to(DEV))
+        ckv = ops.linear_small(cn, mod.to_context[1].weight.detach().to(DEV), None).view(B, Jc, -1)
+    o = ops.linear_attention(qkv.view(B, H * W, -1), 8, mod.scale, ckv)
+    o = ops.conv_gemm(o.view(B, H, W, -1), pack_w(mod.to_out[0].weight.detach()), None, ksize=1)
+    out = ops.layernorm_h16(o, mod.to_out[1].g.detach().reshape(-1).to(DEV))
+    err = rel_l2(from_nhwc(out), ref)
+    print(f"linear attention {B}x{H}x{W} dim {dim} ctx {Jc}: rel_l2 = {err:.3e}")
+    assert err < 5e-3
+    if B > 1:  # batch invariance
+        one = ops.linear_attention(qkv.view(B, H * W, -1)[1:2].contiguous(), 8, mod.scale, None if ckv is None else ckv[1:2].contiguous())
+        full = ops.linear_attention(qkv.view(B, H * W, -1), 8, mod.scale, ckv)
+        assert torch.equal(one[0], full[1])
