@@ -11,6 +11,8 @@ template <int ROWS>
 __global__ void linear_small_kernel(const float* __restrict__ x, int M, int K, long ldx, const float* __restrict__ w,
                                     const float* __restrict__ bias, float* __restrict__ y, int N, long ldy, int pre_act,
                                     int post_act) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
@@ -52,6 +54,8 @@ __global__ void linear_small_kernel(const float* __restrict__ x, int M, int K, l
 }
 
 __global__ void sinu_emb_kernel(const float* __restrict__ t, const float* __restrict__ w, int B, int half, float* __restrict__ out) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int D = 2 * half + 1;
   if (i >= B * D) return;
@@ -73,6 +77,8 @@ __global__ void sinu_emb_kernel(const float* __restrict__ t, const float* __rest
 // kv_out[b] = [ ctx rows (Jc) | null row | token rows (N) ], each row = 64 k values then 64 v values (h16)
 __global__ void kv_assemble_kernel(const h16* __restrict__ qkv, long ld, int kv_col, const float* __restrict__ ctx_kv, int Jc,
                                    const float* __restrict__ null_kv, h16* __restrict__ kv_out, int N) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int b = blockIdx.y;
   const int J = Jc + 1 + N;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, 8-col group): 16 groups per row
@@ -110,6 +116,8 @@ constexpr int AT_BQ = 64, AT_BK = 64, AT_D = 64, AT_PAD = 8;  // smem row = 72 h
 
 __global__ void __launch_bounds__(128) attn_mqa_kernel(const h16* __restrict__ q, long ldq, const h16* __restrict__ kv,
                                                        h16* __restrict__ out, int N, int J, int heads, float scale_log2) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   __shared__ __align__(16) h16 sK[AT_BK][AT_D + AT_PAD];
   __shared__ __align__(16) h16 sV[AT_BK][AT_D + AT_PAD];
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * AT_BQ;
@@ -255,6 +263,8 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(const h16* __restrict__ q
 __global__ void __launch_bounds__(256) attn_cross_kernel(const h16* __restrict__ q, long ldq, const float* __restrict__ kv,
                                                          const float* __restrict__ null_kv, h16* __restrict__ out, int N, int Jc,
                                                          int heads, float scale) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   extern __shared__ float skv[];  // [J][heads][2][64]
   const int b = blockIdx.y;
   const int J = Jc + 1;
@@ -368,8 +378,7 @@ extern "C" int kd_linear_small(const float* x, int M, int K, long ldx, const flo
   KD_REQUIRE(x && w && y && M > 0 && K > 0 && N > 0 && M <= 65536, "kd_linear_small: bad argument (M=%d K=%d N=%d)", M, K, N);
   const int row_groups = kd_ceil_div(M, 8) < 64 ? kd_ceil_div(M, 8) : 64;
   dim3 grid(kd_ceil_div(N, 8), row_groups);
-  linear_small_kernel<8><<<grid, 256, 0, stream>>>(x, M, K, ldx, w, bias, y, N, ldy, pre_act, post_act);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(linear_small_kernel<8>, dim3(grid), dim3(256), 0, stream, x, M, K, ldx, w, bias, y, N, ldy, pre_act, post_act));
   return KD_OK;
 }
 
@@ -377,8 +386,7 @@ extern "C" int kd_sinu_emb(const float* t, const float* weights, int B, int half
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(t && weights && out && B > 0 && half > 0, "kd_sinu_emb: bad argument");
   const int total = B * (2 * half + 1);
-  sinu_emb_kernel<<<kd_ceil_div(total, 128), 128, 0, stream>>>(t, weights, B, half, out);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(sinu_emb_kernel, dim3(kd_ceil_div(total, 128)), dim3(128), 0, stream, t, weights, B, half, out));
   return KD_OK;
 }
 
@@ -388,9 +396,7 @@ extern "C" int kd_kv_assemble(const void* qkv, long ld, int kv_col, const float*
   KD_REQUIRE(qkv && null_kv && kv_out && B > 0 && N > 0 && Jc >= 0 && (Jc == 0 || ctx_kv), "kd_kv_assemble: bad argument");
   KD_REQUIRE(ld % 8 == 0 && kv_col % 8 == 0, "kd_kv_assemble: ld / kv_col must be multiples of 8");
   const long total = (long)(Jc + 1 + N) * 16;
-  kv_assemble_kernel<<<dim3((unsigned)((total + 255) / 256), B), 256, 0, stream>>>(
-      reinterpret_cast<const h16*>(qkv), ld, kv_col, ctx_kv, Jc, null_kv, reinterpret_cast<h16*>(kv_out), N);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(kv_assemble_kernel, dim3((unsigned)((total + 255) / 256), B), dim3(256), 0, stream, reinterpret_cast<const h16*>(qkv), ld, kv_col, ctx_kv, Jc, null_kv, reinterpret_cast<h16*>(kv_out), N));
   return KD_OK;
 }
 
@@ -400,9 +406,7 @@ extern "C" int kd_attn_mqa(const void* q, long ldq, const void* kv, void* out, i
   KD_REQUIRE(q && kv && out && B > 0 && N > 0 && J > 0 && heads > 0, "kd_attn_mqa: bad argument");
   KD_REQUIRE(ldq % 8 == 0, "kd_attn_mqa: ldq must be a multiple of 8");
   dim3 grid(kd_ceil_div(N, AT_BQ), heads, B);
-  attn_mqa_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const h16*>(q), ldq, reinterpret_cast<const h16*>(kv),
-                                            reinterpret_cast<h16*>(out), N, J, heads, scale * 1.4426950408889634f);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(attn_mqa_kernel, dim3(grid), dim3(128), 0, stream, reinterpret_cast<const h16*>(q), ldq, reinterpret_cast<const h16*>(kv), reinterpret_cast<h16*>(out), N, J, heads, scale * 1.4426950408889634f));
   return KD_OK;
 }
 
@@ -421,9 +425,7 @@ extern "C" int kd_attn_cross(const void* q, long ldq, const float* kv, const flo
   }
   const int tokens_per_block = 32 * (8 / heads);
   dim3 grid(kd_ceil_div(N, tokens_per_block), B);
-  attn_cross_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const h16*>(q), ldq, kv, null_kv, reinterpret_cast<h16*>(out), N,
-                                                 Jc, heads, scale);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(attn_cross_kernel, dim3(grid), dim3(256), smem, stream, reinterpret_cast<const h16*>(q), ldq, kv, null_kv, reinterpret_cast<h16*>(out), N, Jc, heads, scale));
   return KD_OK;
 }
 

@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const h16* __restrict__
                                                          const float* __restrict__ w, const h16* __restrict__ wp,
                                                          const float* __restrict__ bias, float* __restrict__ out, int H, int W,
                                                          int Cout) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   extern __shared__ __align__(16) uint8_t fc_smem[];
   constexpr int ACT_BYTES = FC_HH * FC_HW * FC_PIX_STRIDE * 2;  // 27 200
   constexpr int W_BYTES = FC_WCHUNK * 2;                       // 11 520
@@ -261,8 +263,6 @@ extern "C" int kd_final_conv(const void* xa, int Ca, const float* xb, int Cb, co
     configured = true;
   }
   dim3 grid(kd_ceil_div(W, FC_TW), kd_ceil_div(H, FC_TH), B);
-  final_conv_kernel<<<grid, 256, FC_SMEM, stream>>>(reinterpret_cast<const h16*>(xa), Ca, xb, Cb, w, reinterpret_cast<const h16*>(w_split), bias,
-                                                    out, H, W, Cout);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(final_conv_kernel, dim3(grid), dim3(256), FC_SMEM, stream, reinterpret_cast<const h16*>(xa), Ca, xb, Cb, w, reinterpret_cast<const h16*>(w_split), bias, out, H, W, Cout));
   return KD_OK;
 }

@@ -40,6 +40,8 @@ struct InitParams {
 
 template <int BN>
 __global__ void __launch_bounds__(IC_THREADS, 1) init_conv_kernel(const __grid_constant__ CUtensorMap map_w, const InitParams p) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 4 * BN;  // 2 buffers x 2 output rows
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(IC_M >> 4) << 24);
@@ -301,8 +303,7 @@ int launch_init(const CUtensorMap& mw, const InitParams& p, cudaStream_t stream)
     configured = smem;
   }
   const int grid = p.n_units < kd_num_sms() ? p.n_units : kd_num_sms();
-  init_conv_kernel<BN><<<grid, IC_THREADS, smem, stream>>>(mw, p);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(init_conv_kernel<BN>, dim3(grid), dim3(IC_THREADS), smem, stream, mw, p));
   return KD_OK;
 }
 

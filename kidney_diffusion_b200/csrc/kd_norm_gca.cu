@@ -111,6 +111,8 @@ __global__ void gn_apply_kernel(const h16* __restrict__ x, h16* __restrict__ y, 
                                 int G, float src_scale, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ scale_shift, long ss_stride, int Ctot,
                                 int act, int nblk) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int oct = C >> 3;
   const int lanes = blockDim.x / oct;
   const int o = threadIdx.x % oct;
@@ -171,6 +173,8 @@ __global__ void gn_apply_kernel(const h16* __restrict__ x, h16* __restrict__ y, 
 // logits[b, n] = sum_c x[b,n,c] * w[c] + bias : one warp per pixel (two pixels per warp when C = 128).
 __global__ void rowdot_kernel(const h16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                               float* __restrict__ out, long rows, int C) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int oct = C >> 3;
   const int sub = (oct < 32 && (oct & (oct - 1)) == 0) ? oct : 32;  // lanes cooperating on one pixel (power of two)
   const int ppw = 32 / sub;             // pixels per warp
@@ -207,6 +211,8 @@ __device__ __forceinline__ float gca_logit(const float* __restrict__ lg, long p,
 
 __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restrict__ logits, int n_parts, long part_stride, long HW,
                                 int C, int nblk, float* __restrict__ part, float* __restrict__ ml) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   extern __shared__ float sm[];  // max(T, lanes*C) floats
   __shared__ float s_red[32];
   __shared__ float s_m;
@@ -292,6 +298,8 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
 // into smem, each thread sums a fixed quarter of the chunks (fixed order), then the 4 slices are added in fixed order
 __global__ void gca_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ml, int nblk, int C,
                                     float* __restrict__ pooled) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   extern __shared__ float f[];  // [nblk] + [4][64]
   __shared__ float s_red[8];
   __shared__ float s_M, s_L;
@@ -424,6 +432,8 @@ __global__ void gate_residual_kernel(const h16* __restrict__ h, const float* __r
 
 // standalone octet statistics (fallback when the producer kernel could not fuse them)
 __global__ void oct_stats_kernel(const h16* __restrict__ x, long HW, int C, float* __restrict__ partial, int nblk) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   extern __shared__ float sm[];
   const int oct = C >> 3;
   const int lanes = blockDim.x / oct;
@@ -479,6 +489,8 @@ __global__ void oct_stats_kernel(const h16* __restrict__ x, long HW, int C, floa
 // batch image for all octets (thread = fixed octet, `lanes` threads per octet) -> out[b][split][oct]; fixed order throughout
 __global__ void oct_reduce_kernel(const float* __restrict__ partial, int rpt, int tiles, int TB, int n_oct, int NS,
                                   float* __restrict__ out) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   extern __shared__ double sred[];  // [T][2]
   const int b = blockIdx.y, sp = blockIdx.x;
   const int o = threadIdx.x % n_oct, l = threadIdx.x / n_oct;
@@ -552,6 +564,8 @@ __global__ void gn_finalize_oct_kernel(const float* __restrict__ sa, int na, int
                                        float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ scale_shift, long ss_stride,
                                        float2* __restrict__ coef) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
@@ -604,6 +618,8 @@ __global__ void __launch_bounds__(256) gn_reduce_finalize_kernel(const OctSrc a,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ scale_shift, long ss_stride,
                                                                  float2* __restrict__ coef, unsigned int* __restrict__ counter) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   __shared__ double sred[256 * 2];
   __shared__ bool s_last;
   const int b = blockIdx.y;
@@ -700,6 +716,8 @@ __global__ void __launch_bounds__(256) gn_reduce_finalize_kernel(const OctSrc a,
 template <bool F32>
 __global__ void layernorm_kernel(const void* __restrict__ x_, const float* __restrict__ g, const float* __restrict__ bias,
                                  const void* __restrict__ res_, void* __restrict__ y_, long M, int C, float eps) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= M) return;
@@ -925,10 +943,7 @@ extern "C" int kd_gn_apply(const void* x, void* y, int B, long HW, int C, int c_
   KD_REQUIRE(group_size % 8 == 0 && c_offset % 8 == 0, "kd_gn_apply: group_size/c_offset must be multiples of 8");
   const int T = threads_for_oct(C / 8);
   const int nblk = pick_nblk(HW, T / (C / 8), B);
-  gn_apply_kernel<<<dim3(nblk, B), T, 0, stream>>>(reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), HW, C, c_offset,
-                                                   group_size, num_groups, src_scale, mean_rstd, gamma, beta, scale_shift, ss_stride,
-                                                   Ctot, act, nblk);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(gn_apply_kernel, dim3(nblk, B), dim3(T), 0, stream, reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), HW, C, c_offset, group_size, num_groups, src_scale, mean_rstd, gamma, beta, scale_shift, ss_stride, Ctot, act, nblk));
   return KD_OK;
 }
 
@@ -943,8 +958,7 @@ extern "C" int kd_rowdot(const void* x, const float* w, const float* bias, float
   const long cap = (long)kd_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  rowdot_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const h16*>(x), w, bias, out, rows, C);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(rowdot_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, reinterpret_cast<const h16*>(x), w, bias, out, rows, C));
   return KD_OK;
 }
 
@@ -955,8 +969,7 @@ extern "C" int kd_gca_pool(const void* x, const float* logits, int n_parts, int 
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
   const size_t smem = sizeof(float) * (size_t)T * 8;
-  gca_pool_kernel<<<dim3(nblk, B), T, smem, stream>>>(reinterpret_cast<const h16*>(x), logits, n_parts, (long)B * HW, HW, C, nblk, part, ml);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(gca_pool_kernel, dim3(nblk, B), dim3(T), smem, stream, reinterpret_cast<const h16*>(x), logits, n_parts, (long)B * HW, HW, C, nblk, part, ml));
   return KD_OK;
 }
 
@@ -975,8 +988,7 @@ extern "C" int kd_gca_finalize(const float* part, const float* ml, int B, int nb
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(part && ml && pooled && B > 0 && nblk > 0 && C > 0, "kd_gca_finalize: bad argument");
   KD_REQUIRE(nblk <= 8192, "kd_gca_finalize: nblk too large");
-  gca_finalize_kernel<<<dim3(kd_ceil_div(C, 64), B), 256, (nblk + 256) * sizeof(float), stream>>>(part, ml, nblk, C, pooled);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(gca_finalize_kernel, dim3(kd_ceil_div(C, 64), B), dim3(256), (nblk + 256) * sizeof(float), stream, part, ml, nblk, C, pooled));
   return KD_OK;
 }
 
@@ -1004,8 +1016,7 @@ extern "C" int kd_oct_stats(const void* x, int B, long HW, int C, float* partial
   KD_REQUIRE(x && partial && B > 0 && HW > 0 && nblk > 0, "kd_oct_stats: bad argument");
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
-  oct_stats_kernel<<<dim3(nblk, B), T, T * 2 * sizeof(float), stream>>>(reinterpret_cast<const h16*>(x), HW, C, partial, nblk);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(oct_stats_kernel, dim3(nblk, B), dim3(T), T * 2 * sizeof(float), stream, reinterpret_cast<const h16*>(x), HW, C, partial, nblk));
   return KD_OK;
 }
 
@@ -1024,8 +1035,7 @@ extern "C" int kd_oct_reduce(const float* partial, int rpt, int tiles, int TB, i
              "kd_oct_reduce: bad argument");
   const int NS = kd_oct_reduce_splits(rpt, tiles, TB);
   const int T = threads_for_oct(n_oct);
-  oct_reduce_kernel<<<dim3(NS, B), T, T * 2 * sizeof(double), stream>>>(partial, rpt, tiles, TB, n_oct, NS, out);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(oct_reduce_kernel, dim3(NS, B), dim3(T), T * 2 * sizeof(double), stream, partial, rpt, tiles, TB, n_oct, NS, out));
   return KD_OK;
 }
 
@@ -1037,10 +1047,7 @@ extern "C" int kd_gn_finalize_oct(const float* sum_a, int n_oct_a, int ns_a, flo
   KD_REQUIRE(sum_a && mean_rstd && B > 0 && num_groups > 0 && num_groups <= 32 && group_size % 8 == 0 && count > 0 && ns_a > 0,
              "kd_gn_finalize_oct: bad argument");
   KD_REQUIRE(coef == nullptr || (gamma && beta), "kd_gn_finalize_oct: coefficients need gamma and beta");
-  gn_finalize_oct_kernel<<<B, 32 * num_groups, 0, stream>>>(sum_a, n_oct_a, ns_a, scale_a, sum_b, sum_b ? n_oct_b : 0, sum_b ? ns_b : 0,
-                                                            scale_b, num_groups, group_size, count, eps, mean_rstd, gamma, beta,
-                                                            scale_shift, ss_stride, reinterpret_cast<float2*>(coef));
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(gn_finalize_oct_kernel, dim3(B), dim3(32 * num_groups), 0, stream, sum_a, n_oct_a, ns_a, scale_a, sum_b, sum_b ? n_oct_b : 0, sum_b ? ns_b : 0, scale_b, num_groups, group_size, count, eps, mean_rstd, gamma, beta, scale_shift, ss_stride, reinterpret_cast<float2*>(coef)));
   return KD_OK;
 }
 
@@ -1067,9 +1074,7 @@ extern "C" int kd_gn_reduce_finalize(const float* partial_a, int rpt_a, int tile
     b2.NS = kd_oct_reduce_splits(rpt_b, tiles_b, TB_b);
     b2.out = scratch + (size_t)B * a.NS * n_oct_a * 2;
   }
-  gn_reduce_finalize_kernel<<<dim3(a.NS + b2.NS, B), 256, 0, stream>>>(a, b2, num_groups, group_size, count, eps, mean_rstd, gamma, beta,
-                                                                       scale_shift, ss_stride, reinterpret_cast<float2*>(coef), counter);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(gn_reduce_finalize_kernel, dim3(a.NS + b2.NS, B), dim3(256), 0, stream, a, b2, num_groups, group_size, count, eps, mean_rstd, gamma, beta, scale_shift, ss_stride, reinterpret_cast<float2*>(coef), counter));
   return KD_OK;
 }
 
@@ -1077,8 +1082,7 @@ extern "C" int kd_layernorm_h16(const void* x, const float* g, const float* bias
                                  float eps, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(x && g && y && M > 0 && C > 0 && C % 8 == 0, "kd_layernorm_h16: bad argument (C=%d)", C);
-  layernorm_kernel<false><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(x, g, bias, residual, y, M, C, eps);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(layernorm_kernel<false>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, stream, x, g, bias, residual, y, M, C, eps));
   return KD_OK;
 }
 
@@ -1086,7 +1090,6 @@ extern "C" int kd_layernorm_f32(const float* x, const float* g, const float* bia
                                 kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(x && g && y && M > 0 && C > 0, "kd_layernorm_f32: bad argument");
-  layernorm_kernel<true><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(x, g, bias, nullptr, y, M, C, eps);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(layernorm_kernel<true>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, stream, x, g, bias, nullptr, y, M, C, eps));
   return KD_OK;
 }

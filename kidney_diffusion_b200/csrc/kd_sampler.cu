@@ -22,6 +22,8 @@ struct SelState {
 };
 
 __global__ void sel_init_kernel(SelState* st, uint32_t* hist, int B, uint32_t rank_lo, uint32_t rank_hi) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     st[i].prefix[0] = st[i].prefix[1] = 0u;
@@ -33,6 +35,8 @@ __global__ void sel_init_kernel(SelState* st, uint32_t* hist, int B, uint32_t ra
 
 __global__ void sel_hist_kernel(const float* __restrict__ x_t, const float* __restrict__ pred, long n_per, int objective,
                                 float alpha, float sigma, const SelState* __restrict__ st, uint32_t* __restrict__ hist, int pass) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   __shared__ uint32_t sh[512];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 512; i += blockDim.x) sh[i] = 0u;
@@ -56,6 +60,8 @@ __global__ void sel_hist_kernel(const float* __restrict__ x_t, const float* __re
 }
 
 __global__ void sel_scan_kernel(SelState* st, uint32_t* hist, int pass) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int b = blockIdx.x;
   const int which = threadIdx.x;  // 2 threads
   if (which >= 2) return;
@@ -76,6 +82,8 @@ __global__ void sel_scan_kernel(SelState* st, uint32_t* hist, int pass) {
 }
 
 __global__ void sel_final_kernel(const SelState* st, int B, float weight, float* s_out) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float lo = __uint_as_float(st[b].prefix[0]);
@@ -105,6 +113,8 @@ __device__ __forceinline__ float step_one(float x, float pr, float nz, float s, 
 __global__ void ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ pred, const float* __restrict__ noise,
                                  const float* __restrict__ s_dev, float* __restrict__ out, float* __restrict__ x0_out,
                                  const float* __restrict__ renoise, long n_per, StepArgs a) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int b = blockIdx.y;
   const float s = s_dev ? s_dev[b] : 1.0f;
   const long base = (long)b * n_per;
@@ -134,6 +144,8 @@ __global__ void ddpm_step_kernel(const float* __restrict__ x_t, const float* __r
 
 __global__ void inpaint_blend_kernel(float* __restrict__ img, const float* __restrict__ inpaint, const uint8_t* __restrict__ mask,
                                      const float* __restrict__ noise, float alpha, float sigma, int C, long HW) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const int b = blockIdx.y;
   const long n = (long)C * HW;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -177,6 +189,8 @@ __device__ __forceinline__ void philox_round(uint32_t* c, uint32_t k0, uint32_t 
 }
 
 __global__ void randn_kernel(float* __restrict__ out, long n, uint64_t seed, uint64_t key) {
+  kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
+  kd_pdl_trigger();
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += stride) {
     uint32_t c[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)key, (uint32_t)(key >> 32)};
@@ -264,19 +278,15 @@ extern "C" int kd_dynthresh(const float* x_t, const float* pred, int B, long n_p
   KD_REQUIRE(rank_lo >= 0 && rank_hi >= rank_lo && rank_hi < n_per && n_per < 4294967296L, "kd_dynthresh: bad ranks");
   uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
   SelState* st = reinterpret_cast<SelState*>(hist + (size_t)B * 512);
-  sel_init_kernel<<<kd_ceil_div((long)B * 512, 256), 256, 0, stream>>>(st, hist, B, (uint32_t)rank_lo, (uint32_t)rank_hi);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(sel_init_kernel, dim3(kd_ceil_div((long)B * 512, 256)), dim3(256), 0, stream, st, hist, B, (uint32_t)rank_lo, (uint32_t)rank_hi));
   long blocks = (n_per + 256L * 8 - 1) / (256L * 8);
   const long cap = (long)kd_num_sms() * 8 / B + 1;
   if (blocks > cap) blocks = cap;
   for (int pass = 0; pass < 4; ++pass) {
-    sel_hist_kernel<<<dim3((unsigned)blocks, B), 256, 0, stream>>>(x_t, pred, n_per, objective, alpha, sigma, st, hist, pass);
-    KD_LAUNCH_CHECK();
-    sel_scan_kernel<<<B, 32, 0, stream>>>(st, hist, pass);
-    KD_LAUNCH_CHECK();
+    KD_CUDA(kd_launch(sel_hist_kernel, dim3((unsigned)blocks, B), dim3(256), 0, stream, x_t, pred, n_per, objective, alpha, sigma, st, hist, pass));
+    KD_CUDA(kd_launch(sel_scan_kernel, dim3(B), dim3(32), 0, stream, st, hist, pass));
   }
-  sel_final_kernel<<<kd_ceil_div(B, 64), 64, 0, stream>>>(st, B, weight, s_out);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(sel_final_kernel, dim3(kd_ceil_div(B, 64)), dim3(64), 0, stream, st, B, weight, s_out));
   return KD_OK;
 }
 
@@ -291,8 +301,7 @@ extern "C" int kd_ddpm_step(const float* x_t, const float* pred, const float* no
   long blocks = (n_per / 4 + 255) / 256;
   const long cap = (long)kd_num_sms() * 8 / B + 1;
   if (blocks > cap) blocks = cap;
-  ddpm_step_kernel<<<dim3((unsigned)blocks, B), 256, 0, stream>>>(x_t, pred, noise, s, out, x0_out, renoise, n_per, a);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(ddpm_step_kernel, dim3((unsigned)blocks, B), dim3(256), 0, stream, x_t, pred, noise, s, out, x0_out, renoise, n_per, a));
   return KD_OK;
 }
 
@@ -300,8 +309,7 @@ extern "C" int kd_inpaint_blend(float* img, const float* inpaint, const uint8_t*
                                 int B, int C, long HW, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(img && inpaint && mask && B > 0 && C > 0 && HW > 0, "kd_inpaint_blend: bad argument");
-  inpaint_blend_kernel<<<dim3(ew_blocks((long)C * HW / 2), B), 256, 0, stream>>>(img, inpaint, mask, noise, alpha, sigma, C, HW);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(inpaint_blend_kernel, dim3(ew_blocks((long)C * HW / 2), B), dim3(256), 0, stream, img, inpaint, mask, noise, alpha, sigma, C, HW));
   return KD_OK;
 }
 
@@ -324,8 +332,7 @@ extern "C" int kd_q_sample(const float* x0, const float* noise, float alpha, flo
 extern "C" int kd_randn(float* out, long n, uint64_t seed, uint64_t key, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KD_REQUIRE(out && n > 0, "kd_randn: bad argument");
-  randn_kernel<<<ew_blocks(n / 4 + 1), 256, 0, stream>>>(out, n, seed, key);
-  KD_LAUNCH_CHECK();
+  KD_CUDA(kd_launch(randn_kernel, dim3(ew_blocks(n / 4 + 1)), dim3(256), 0, stream, out, n, seed, key));
   return KD_OK;
 }
 
