@@ -27,7 +27,10 @@ DEFAULT_STEP_MS = {
     2: {1: 4.5, 2: 4.6, 4: 5.4, 8: 6.8, 16: 10.2, 32: 18.4, 64: 35.4},
     3: {1: 15.0, 2: 26.9, 4: 50.8, 8: 97.9, 16: 192.6, 32: 383.5},
 }
-ALLOWED_BATCH = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32)      # batch sizes a plan may use (bounds the number of captured CUDA graphs)
+# batch sizes a plan may use (bounds the number of captured CUDA graphs): fine for the small launch-bound stages, where taking a
+# whole anti-diagonal (up to 21 patches on the 21 x 21 grid) in ONE batch matters; coarse for the 1024^2 stage (3.3 GB per patch)
+ALLOWED_BATCH = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
+ALLOWED_BATCH_SMALL = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 21, 24, 28, 32)
 DEFAULT_MAX_BATCH = {1: 32, 2: 16, 3: 16}                # per stage (64^2 / 256^2 / 1024^2): memory- and latency-driven caps
 FULL_STEPS = {1: 1024, 2: 256, 3: 256}                   # train_ultra_res_v_param.py:86
 
@@ -95,9 +98,9 @@ class Plan:
         return busy / (self.world * self.makespan) if self.makespan > 0 else 1.0
 
 
-def _floor_allowed(n, cap):
+def _floor_allowed(n, cap, stage=3):
     best = 1
-    for b in ALLOWED_BATCH:
+    for b in (ALLOWED_BATCH if stage >= 3 else ALLOWED_BATCH_SMALL):
         if b <= n and b <= cap:
             best = b
     return best
@@ -144,7 +147,7 @@ def _simulate(patch_pos, orientation, world, stages, unit_cost, max_batch, pack_
         else:  # share what is ready among the ranks that are idle right now
             idle = sum(1 for q in range(world) if free_at[q] <= t_now + eps)
             cap = min(max_batch[u], max(1, -(-len(cand) // idle)))
-        take = cand[:_floor_allowed(len(cand), cap)]
+        take = cand[:_floor_allowed(len(cand), cap, u)]
         end = t_now + cost_fn(u, len(take))
         batches.append(Batch(u, [t[1] for t in take], r, t_now, end))
         free_at[r] = end
