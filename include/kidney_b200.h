@@ -196,6 +196,12 @@ int kd_kv_assemble(const void* qkv /* fp16 [B,N,ld] */, long ld, int kv_col, con
                    const float* null_kv /* [2,64] */, void* kv_out /* fp16 [B, Jc+1+N, 128] */, int B, int N, kd_stream_t stream);
 int kd_attn_mqa(const void* q /* fp16 [B,N,*] */, long ldq, const void* kv /* fp16 [B,J,128] */, void* out /* fp16 [B,N,heads*64] */,
                 int B, int N, int J, int heads, float scale, kd_stream_t stream);
+/* kd_attn_mqa on the 5th-gen tensor cores (tcgen05.mma with S and PV accumulators in TMEM, Q / K / V^T tiles by TMA, online softmax
+ * in registers; csrc/kd_attn_tc.cu), used for N >= 256 tokens.  vt_scratch: kd_attn_vt_elems(B, J) fp16 elements of caller-owned
+ * scratch (the kernel first writes V^T there: the K-major B operand of the P V product). */
+int kd_attn_vt_elems(int B, int J);
+int kd_attn_mqa_tc(const void* q, long ldq, const void* kv, void* vt_scratch, void* out, int B, int N, int J, int heads, float scale,
+                   kd_stream_t stream);
 int kd_attn_cross(const void* q, long ldq, const float* kv /* [B,Jc,2*heads*64] */, const float* null_kv /* [2,64] */,
                   void* out /* fp16 [B,N,heads*64] */, int B, int N, int Jc, int heads, float scale, kd_stream_t stream);
 

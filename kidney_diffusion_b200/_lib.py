@@ -64,6 +64,8 @@ SIGNATURES = {
     "kd_layernorm_f32": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "kd_kv_assemble": (c_int, [_P, _L, _I, _P, _I, _P, _P, _I, _I, _P]),
     "kd_attn_mqa": (c_int, [_P, _L, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "kd_attn_vt_elems": (c_int, [_I, _I]),
+    "kd_attn_mqa_tc": (c_int, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "kd_attn_cross": (c_int, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "kd_attn_small_f32": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "kd_axpby": (c_int, [_P, _P, _F, _F, _P, _L, _P]),

@@ -494,12 +494,20 @@ def kv_assemble(qkv, kv_col, ctx_kv, null_kv):
     return out
 
 
+ATTN_TC_MIN_TOKENS = 256  # kd_attn_mqa_tc (tcgen05) from this many query tokens; below, the mma.sync kernel (tests may raise it)
+
+
 @_timed
 def attn_mqa(q, kv, heads, scale):
     """q: fp16 [B,N,ld] (first heads*64 columns are the queries); kv: fp16 [B,J,128]."""
     B, N, ld = q.shape
     J = kv.shape[1]
     out = torch.empty((B, N, heads * 64), device=q.device, dtype=ACT_DTYPE)
+    if N >= ATTN_TC_MIN_TOKENS:  # tcgen05 kernel (choice by the per-sample token count only: batch-invariant)
+        vt = torch.empty((lib().kd_attn_vt_elems(B, J),), device=q.device, dtype=ACT_DTYPE)
+        check(lib().kd_attn_mqa_tc(_ptr(q), ld, _ptr(kv), _ptr(vt), _ptr(out), B, N, J, heads, scale, _stream()), "kd_attn_mqa_tc")
+        _count(2)
+        return out
     check(lib().kd_attn_mqa(_ptr(q), ld, _ptr(kv), _ptr(out), B, N, J, heads, scale, _stream()), "kd_attn_mqa")
     _count()
     return out

@@ -77,7 +77,9 @@ elif target == "gca_pool":  # gca_pool_kernel on the 512^2 x 128 tensor (HBM-bou
     x = act(B, S, S, 128)
     logits = torch.randn(2, B, S * S, device=dev)
     run(lambda: ops.gca_pool(x, logits), 0.0, B * S * S * (256 + 8))
-elif target == "attn":      # attn_mqa_kernel: N = 4096 tokens, 8 heads of 64, multi-query
+elif target == "attn":      # attn_mqa_tc_kernel (tcgen05; set KD_ATTN_LEGACY=1 for the mma.sync kernel): N = 4096 tokens, 8 heads of 64, multi-query
+    if os.environ.get("KD_ATTN_LEGACY"):
+        ops.ATTN_TC_MIN_TOKENS = 1 << 30
     N = 4096
     qkv = act(B, N, 512 + 128)
     kv = ops.kv_assemble(qkv, 512, None, torch.randn(2, 64, device=dev))

@@ -882,3 +882,36 @@ def test_linear_attention_block_matches_oracle(cuda_lib, B, H, W, dim, Jc):
         one = ops.linear_attention(qkv.view(B, H * W, -1)[1:2].contiguous(), 8, mod.scale, None if ckv is None else ckv[1:2].contiguous())
         full = ops.linear_attention(qkv.view(B, H * W, -1), 8, mod.scale, ckv)
         assert torch.equal(one[0], full[1])
+
+
+@pytest.mark.parametrize("B,N,Jc", [(2, 256, 0), (1, 1000, 5), (1, 4096, 0), (3, 384, 36)])
+def test_attn_mqa_tcgen05_matches_mma_sync_kernel(cuda_lib, B, N, Jc):
+    """kd_attn_mqa_tc (tcgen05 / TMEM / TMA, N >= 256) against the legacy mma.sync flash kernel and the fp32 definition: ragged
+    query tiles (N = 1000), key counts that are not multiples of 8 or 128 (null + context rows), batch invariance."""
+    from kidney_diffusion_b200 import ops
+
+    g = torch.Generator().manual_seed(N + Jc + B)
+    heads, d = 8, 64
+    qkv = rb(torch.randn(B, N, heads * d + 2 * d, generator=g) * 1.5)
+    ctx = torch.randn(B, Jc, 2 * d, generator=g) if Jc else None
+    null_kv = torch.randn(2, d, generator=g)
+    dq = bf(qkv).to(DEV)
+    kv = ops.kv_assemble(dq, heads * d, None if ctx is None else ctx.to(DEV), null_kv.to(DEV))
+    out_tc = ops.attn_mqa(dq, kv, heads, d ** -0.5)
+    saved = ops.ATTN_TC_MIN_TOKENS
+    try:
+        ops.ATTN_TC_MIN_TOKENS = 1 << 30
+        out_legacy = ops.attn_mqa(dq, kv, heads, d ** -0.5)
+    finally:
+        ops.ATTN_TC_MIN_TOKENS = saved
+    torch.cuda.synchronize()
+    q = qkv[..., : heads * d].view(B, N, heads, d).transpose(1, 2) * d ** -0.5
+    kf, vf = kv[..., :d].float().cpu(), kv[..., d:].float().cpu()
+    attn = torch.einsum("bhid,bjd->bhij", q, kf).softmax(-1)
+    ref = torch.einsum("bhij,bjd->bhid", attn, vf).transpose(1, 2).reshape(B, N, heads * d)
+    e_tc, e_leg = rel_l2(out_tc, ref), rel_l2(out_legacy, ref)
+    print(f"attn N={N} J={kv.shape[1]}: tcgen05 {e_tc:.3e}, mma.sync {e_leg:.3e}")
+    assert bool(torch.isfinite(out_tc).all()) and e_tc < 4e-3 and rel_l2(out_tc, out_legacy) < 4e-3
+    if B > 1:
+        one = ops.attn_mqa(dq[1:2].contiguous(), kv[1:2].contiguous(), heads, d ** -0.5)
+        assert torch.equal(one[0], out_tc[1])
