@@ -29,6 +29,58 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                : "memory");
 }
 
+// One 128-key tile of one query row: tile max -> running max, P = exp2((S - m) c) as fp16 into the swizzled A-operand tile.
+// MASK: only the last tile of a sequence has fewer than 128 valid keys; the full tiles run without per-element predicates.
+template <bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t t_row, uint32_t p_s, int r, int valid, float scale_log2, float& m_run, float& corr,
+                                             float& lsum) {
+  float tmax = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; c += 2) {  // two 32-column loads in flight per wait
+    uint32_t sv[2][32];
+    tmem_ld32(t_row + (uint32_t)(c * 32), sv[0]);
+    tmem_ld32(t_row + (uint32_t)(c * 32 + 32), sv[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (!MASK || (c + u) * 32 + j < valid) tmax = fmaxf(tmax, __uint_as_float(sv[u][j]));
+  }
+  const float m_new = fmaxf(m_run, tmax);
+  const float mc = m_new * scale_log2;
+  corr = ex2_fast((m_run - m_new) * scale_log2);  // m_run = -inf on the first tile: exp2(-inf) = 0
+  m_run = m_new;
+  lsum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t sv[32];
+    tmem_ld32(t_row + (uint32_t)(c * 32), sv);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float p0 = ex2_fast(fmaf(__uint_as_float(sv[j]), scale_log2, -mc));
+      float p1 = ex2_fast(fmaf(__uint_as_float(sv[j + 1]), scale_log2, -mc));
+      if (MASK) {
+        if (c * 32 + j >= valid) p0 = 0.f;
+        if (c * 32 + j + 1 >= valid) p1 = 0.f;
+      }
+      lsum += p0 + p1;
+      pk[j >> 1] = pack_h16x2(p0, p1);
+    }
+    // P as a K-major, 128B-swizzled A operand: block = c / 2 (64 keys each), 16-byte chunk = (c & 1) * 4 + q
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
+      const uint32_t dst = p_s + (uint32_t)(c >> 1) * TA_TILE_BYTES + (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
+                   "r"(pk[4 * q + 3])
+                   : "memory");
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TA_THREADS, 2)
 attn_mqa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_vt, h16* __restrict__ out, int N, int J, int heads, float scale_log2) {
@@ -134,63 +186,30 @@ attn_mqa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
     for (int j = 0; j < TA_D; ++j) o[j] = 0.f;
     for (int t = 0; t < T; ++t) {
-      mbar_wait_relaxed(smem_u32(s_full), (uint32_t)t & 1u);
+      mbar_wait(smem_u32(s_full), (uint32_t)t & 1u);
       tc_fence_after();
       const int valid = min(TA_BK, J - t * TA_BK);  // keys of this tile that exist (>= 1)
-      float tmax = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(t_row + (uint32_t)(c * 32), sv);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < valid) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
-      }
-      const float m_new = fmaxf(m_run, tmax);
-      const float mc = m_new * scale_log2;
-      const float corr = ex2_fast((m_run - m_new) * scale_log2);  // m_run = -inf on the first tile: exp2(-inf) = 0
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(t_row + (uint32_t)(c * 32), sv);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = (c * 32 + j < valid) ? ex2_fast(fmaf(__uint_as_float(sv[j]), scale_log2, -mc)) : 0.f;
-          const float p1 = (c * 32 + j + 1 < valid) ? ex2_fast(fmaf(__uint_as_float(sv[j + 1]), scale_log2, -mc)) : 0.f;
-          lsum += p0 + p1;
-          pk[j >> 1] = pack_h16x2(p0, p1);
-        }
-        // P as a K-major, 128B-swizzled A operand: block = c / 2 (64 keys each), 16-byte chunk = (c & 1) * 4 + q
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
-          const uint32_t dst = p_s + (uint32_t)(c >> 1) * TA_TILE_BYTES + (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
-                       "r"(pk[4 * q + 3])
-                       : "memory");
-        }
-      }
+      float corr, lsum;
+      if (valid == TA_BK) softmax_tile<false>(t_row, p_s, r, valid, scale_log2, m_run, corr, lsum);   // full tile: no per-element predicates
+      else softmax_tile<true>(t_row, p_s, r, valid, scale_log2, m_run, corr, lsum);
       l_run = fmaf(l_run, corr, lsum);
-      m_run = m_new;
 #pragma unroll
       for (int j = 0; j < TA_D; ++j) o[j] *= corr;
       tc_fence_before();
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(p_ready));
-      mbar_wait_relaxed(smem_u32(pv_full), (uint32_t)t & 1u);
+      mbar_wait(smem_u32(pv_full), (uint32_t)t & 1u);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pv[32];
-        tmem_ld32(t_row + 128u + (uint32_t)(c * 32), pv);
+      {
+        uint32_t pv[2][32];
+        tmem_ld32(t_row + 128u, pv[0]);
+        tmem_ld32(t_row + 160u, pv[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[c * 32 + j] += __uint_as_float(pv[j]);
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[c * 32 + j] += __uint_as_float(pv[c][j]);
       }
       tc_fence_before();
     }
