@@ -42,6 +42,11 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):  # tcgen05.mma, TMA tensor load, tcgen05.ld
         assert mnemonic in sass, mnemonic
+    # the attention kernel is a tcgen05 kernel too ("SASS of the attention kernel shows UTCHMMA and LDTM")
+    obj = os.path.join(os.path.dirname(_lib.LIB_PATH), "build", "kd_attn_tc.o")
+    if os.path.exists(obj):
+        attn = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+        assert "UTCHMMA" in attn and "LDTM" in attn and "UTMALDG" in attn
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
