@@ -743,10 +743,10 @@ def stitch_device(zoomed_image, patches, patch_pos, num_patches_width, overlap, 
         for k, (i, j) in enumerate(patch_pos):
             ops.patch_paste(patches[k].to(device).reshape(3, PATCH_SIZE, PATCH_SIZE).contiguous(), canvas.data_ptr(), Wc, cell, n, patch_dist, k, i, j)
         return canvas
-    from .grid_exec import try_peer_mailbox
+    from .grid_exec import _CANVAS_CACHE, cached_peer_mailbox
 
     incoming = {r: [(("canvas",), (3, Wc, Wc))] + [(("done", s), (1, 1, 1)) for s in range(world) if s != r] for r in range(world)}
-    box = try_peer_mailbox(dist, rank, world, device, incoming)
+    box = cached_peer_mailbox(dist, rank, world, device, incoming, max_entries=1, cache=_CANVAS_CACHE)
     if box is None:  # NCCL fallback: gather on rank 0, stitch there, broadcast
         full = gather_patches(patches)
         canvas = torch.empty((1, 3, Wc, Wc), device=device, dtype=torch.float32)
@@ -773,7 +773,7 @@ def stitch_device(zoomed_image, patches, patch_pos, num_patches_width, overlap, 
     own = box.own[off[rank] // 4: off[rank] // 4 + 3 * Wc * Wc].view(1, 3, Wc, Wc)
     canvas = own.clone()
     box.finish()
-    box.close()
+    box.recycle()  # barrier: every rank has cloned its canvas before anybody pastes the next image into it
     return canvas
 
 

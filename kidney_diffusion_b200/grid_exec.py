@@ -200,16 +200,20 @@ def try_peer_mailbox(dist, rank, world, device, incoming):
 _BOX_CACHE = {}
 
 
-def cached_peer_mailbox(dist, rank, world, device, incoming, max_entries=4):
+def cached_peer_mailbox(dist, rank, world, device, incoming, max_entries=4, cache=None):
     """Plan mailboxes are reused between runs with the same message layout (allocation + IPC mapping cost ~0.1 s); all ranks
     call this with identical arguments in the same order, so cache hits, misses and evictions are collective."""
+    cache = _BOX_CACHE if cache is None else cache
     key = (world, str(device), repr(sorted((r, tuple(m)) for r, m in incoming.items())))
-    box = _BOX_CACHE.get(key)
+    box = cache.get(key)
     if box is not None:
         return box
-    while len(_BOX_CACHE) >= max_entries:
-        _BOX_CACHE.pop(next(iter(_BOX_CACHE))).close()
+    while len(cache) >= max_entries:
+        cache.pop(next(iter(cache))).close()
     box = try_peer_mailbox(dist, rank, world, device, incoming)
     if box is not None:
-        _BOX_CACHE[key] = box
+        cache[key] = box
     return box
+
+
+_CANVAS_CACHE = {}  # the stitch canvases (3.2 GB per rank at 16 384^2) are kept for the next image of the same size
