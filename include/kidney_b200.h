@@ -211,7 +211,8 @@ int kd_attn_cross(const void* q, long ldq, const float* kv /* [B,Jc,2*heads*64] 
  *                       q|k|v map, NHWC fp16; w fp32 [C][3][3];
  *   kd_linattn_context: k <- softmax over positions (N pixels of columns [k_col, k_col+heads*64) of `qkv` plus J fp32 context-token
  *                       rows ctx_kv [B][J][2*heads*64] = k | v), ctx[b][h][d][e] = sum_n k[n,h,d] v[n,h,e] (fp32 [B][heads][64][64]);
- *                       pixel chunks are reduced in fixed order (chunk count = kd_linattn_blocks(N), independent of B);
+ *                       pixel chunks are reduced in fixed order (chunk count = kd_linattn_blocks(N), independent of B); N = 0 = tokens
+ *                       only (LinearCrossAttention);
  *   kd_linattn_apply  : out[n, h*64+e] = act(scale * sum_d softmax_d(q[n,h,:])[d] * ctx[h][d][e]), fp16 [B][N][heads*64].
  * The products are 64 x 64 per head (no tensor-core tile fits); the block is bound by one pass over q, k and v. */
 int kd_dwconv3x3(const void* x, const float* w, void* y, int B, int H, int W, int C, kd_stream_t stream);

@@ -208,7 +208,8 @@ extern "C" int kd_linattn_blocks(int N) {
 extern "C" int kd_linattn_context(const void* qkv, long ld, int k_col, int v_col, int B, int N, int heads, const float* ctx_kv, int J,
                                   float* workspace, size_t ws_bytes, float* ctx, kd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KD_REQUIRE(qkv && workspace && ctx && B > 0 && N > 0 && heads > 0 && J >= 0 && (J == 0 || ctx_kv), "kd_linattn_context: bad argument");
+  KD_REQUIRE(qkv && workspace && ctx && B > 0 && N >= 0 && heads > 0 && J >= 0 && N + J > 0 && (J == 0 || ctx_kv),
+             "kd_linattn_context: bad argument");
   KD_REQUIRE(ld % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0, "kd_linattn_context: ld / column offsets must be multiples of 8");
   const int nblk = kd_linattn_blocks(N), inner = heads * LA_D;
   const size_t need = sizeof(float) * ((size_t)B * nblk * inner + (size_t)B * heads * nblk * (LA_D * LA_D + LA_D));

@@ -197,9 +197,10 @@ class LinearAttentionTransformerBlock(_NoCall):
 
 
 class ResnetBlock(_NoCall):
-    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, use_gca=False, **attn_kwargs):
+    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, linear_attn=False, use_gca=False, **attn_kwargs):
         super().__init__()
         self.dim, self.dim_out, self.groups = dim, dim_out, groups
+        self.linear_cross_attn = bool(linear_attn) and exists(cond_dim)  # LinearCrossAttention: same parameters, different forward
         self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_cond_dim, dim_out * 2)) if exists(time_cond_dim) else None
         self.cross_attn = (
             EinopsToAndFrom(CrossAttention(dim=dim_out, context_dim=cond_dim, **attn_kwargs)) if exists(cond_dim) else None

@@ -550,22 +550,25 @@ def dwconv3x3(x, w):
 
 
 @_timed
-def linear_attention(qkv, heads, scale, ctx_kv=None, act=ACT_SILU):
-    """qkv: fp16 [B, N, 3*heads*64] (q | k | v after the depthwise convs); ctx_kv: fp32 [B, J, 2*heads*64] (k | v of the context
-    tokens) or None -> fp16 [B, N, heads*64] = act(scale * softmax_d(q) @ (softmax_n(k)^T v))."""
+def linear_attention(qkv, heads, scale, ctx_kv=None, act=ACT_SILU, pixels_kv=True):
+    """qkv: fp16 [B, N, 3*heads*64] (q | k | v after the depthwise convs), or with pixels_kv=False only the queries [B, N, heads*64];
+    ctx_kv: fp32 [B, J, 2*heads*64] (k | v of the context tokens) or None -> fp16 [B, N, heads*64] = act(scale * softmax_d(q) @
+    (softmax_n(k)^T v)), n running over the pixels (pixels_kv) and the tokens."""
     _chk(qkv, ACT_DTYPE, "qkv")
     B, N, ld = qkv.shape
     inner = heads * 64
-    assert ld == 3 * inner
+    assert ld == (3 * inner if pixels_kv else inner)
     J = 0
     if ctx_kv is not None:
         _chk(ctx_kv, torch.float32, "ctx_kv")
         J = ctx_kv.shape[1]
         assert ctx_kv.shape == (B, J, 2 * inner)
-    nbytes = lib().kd_linattn_workspace_bytes(B, N, heads)
+    n_kv = N if pixels_kv else 0
+    assert n_kv + J > 0
+    nbytes = lib().kd_linattn_workspace_bytes(B, n_kv, heads)
     ws = torch.empty((nbytes,), device=qkv.device, dtype=torch.uint8)
     ctx = torch.empty((B, heads, 64, 64), device=qkv.device, dtype=torch.float32)
-    check(lib().kd_linattn_context(_ptr(qkv), ld, inner, 2 * inner, B, N, heads, _ptr(ctx_kv), J, _ptr(ws), nbytes, _ptr(ctx), _stream()),
+    check(lib().kd_linattn_context(_ptr(qkv), ld, inner, 2 * inner, B, n_kv, heads, _ptr(ctx_kv), J, _ptr(ws), nbytes, _ptr(ctx), _stream()),
           "kd_linattn_context")
     out = torch.empty((B, N, inner), device=qkv.device, dtype=ACT_DTYPE)
     check(lib().kd_linattn_apply(_ptr(qkv), ld, 0, _ptr(ctx), _ptr(out), B, N, heads, scale, act, _stream()), "kd_linattn_apply")

@@ -32,7 +32,7 @@ class Unet(nn.Module):
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
         unsupported = dict(
-            use_linear_cross_attn=use_linear_cross_attn, cross_embed_downsample=cross_embed_downsample,
+            cross_embed_downsample=cross_embed_downsample,
             self_cond=self_cond, combine_upsample_fmaps=combine_upsample_fmaps,
         )
         for k, v in unsupported.items():
@@ -108,10 +108,11 @@ class Unet(nn.Module):
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
         use_linear_attn = cast_tuple(use_linear_attn, num_layers)
-        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns, use_linear_attn]
+        use_linear_cross_attn = cast_tuple(use_linear_cross_attn, num_layers)
+        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns, use_linear_attn, use_linear_cross_attn]
         reversed_layer_params = [tuple(reversed(p)) for p in layer_params]
         skip_connect_dims = []
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(zip(in_out, *layer_params)):
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin, layer_lin_cross) in enumerate(zip(in_out, *layer_params)):
             is_last = ind >= (num_layers - 1)
             layer_cond_dim = cond_dim if layer_cross_attn else None
             current_dim = dim_in
@@ -130,7 +131,7 @@ class Unet(nn.Module):
                 nn.ModuleList(
                     [
                         pre_downsample,
-                        ResnetBlock(current_dim, current_dim, cond_dim=layer_cond_dim, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
+                        ResnetBlock(current_dim, current_dim, cond_dim=layer_cond_dim, linear_attn=layer_lin_cross, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
                         nn.ModuleList(
                             [ResnetBlock(current_dim, current_dim, time_cond_dim=time_cond_dim, groups=groups, use_gca=use_global_context_attn)
                              for _ in range(n_blocks)]
@@ -146,7 +147,7 @@ class Unet(nn.Module):
         self.mid_block1 = ResnetBlock(mid_dim, mid_dim, cond_dim=cond_dim, time_cond_dim=time_cond_dim, groups=resnet_groups[-1], **attn_kwargs)
         self.mid_attn = TransformerBlock(mid_dim, depth=layer_mid_attns_depth, **attn_kwargs) if attend_at_middle else None
         self.mid_block2 = ResnetBlock(mid_dim, mid_dim, cond_dim=cond_dim, time_cond_dim=time_cond_dim, groups=resnet_groups[-1], **attn_kwargs)
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin, layer_lin_cross) in enumerate(
             zip(reversed(in_out), *reversed_layer_params)
         ):
             is_last = ind == (len(in_out) - 1)
@@ -155,7 +156,7 @@ class Unet(nn.Module):
             self.ups.append(
                 nn.ModuleList(
                     [
-                        ResnetBlock(dim_out + skip_connect_dim, dim_out, cond_dim=layer_cond_dim, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
+                        ResnetBlock(dim_out + skip_connect_dim, dim_out, cond_dim=layer_cond_dim, linear_attn=layer_lin_cross, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
                         nn.ModuleList(
                             [ResnetBlock(dim_out + skip_connect_dim, dim_out, time_cond_dim=time_cond_dim, groups=groups, use_gca=use_global_context_attn)
                              for _ in range(n_blocks)]

@@ -74,7 +74,7 @@ class _Res:
         if exists(m.cross_attn):
             a = m.cross_attn.fn
             self.xattn = dict(
-                heads=a.heads, scale=a.scale, norm_g=a.norm.g.detach().reshape(-1).contiguous(), null_kv=a.null_kv.detach(),
+                linear=getattr(m, "linear_cross_attn", False), heads=a.heads, scale=a.scale, norm_g=a.norm.g.detach().reshape(-1).contiguous(), null_kv=a.null_kv.detach(),
                 wq=_pack_conv(a.to_q.weight), wkv=a.to_kv.weight.detach(), wo=_pack_conv(a.to_out[0].weight),
                 out_g=a.to_out[1].g.detach().reshape(-1).contiguous(),
             )
@@ -366,7 +366,13 @@ class UnetExecutor:
         xn = ops.layernorm_h16(h, P["norm_g"])
         q = ops.conv_gemm(xn, P["wq"], None, ksize=1)
         kv = ops.linear_small(c.view(B * J, -1), P["wkv"]).view(B, J, -1)
-        o = ops.attn_cross(q.view(B, H * W, -1), kv, P["null_kv"], P["heads"], P["scale"])
+        if P["linear"]:  # LinearCrossAttention: softmax_d(q) @ (softmax_tokens(k)^T v) over the null + context tokens
+            inner = P["heads"] * 64
+            null_row = torch.cat((P["null_kv"][0].float().repeat(P["heads"]), P["null_kv"][1].float().repeat(P["heads"])))  # k | v, every head
+            tokens = torch.cat((null_row.view(1, 1, 2 * inner).expand(B, 1, 2 * inner), kv), 1).contiguous()
+            o = ops.linear_attention(q.view(B, H * W, -1), P["heads"], P["scale"], tokens, act=ops.ACT_NONE, pixels_kv=False)
+        else:
+            o = ops.attn_cross(q.view(B, H * W, -1), kv, P["null_kv"], P["heads"], P["scale"])
         o = ops.conv_gemm(o.view(B, H, W, -1), P["wo"], None, ksize=1)
         return ops.layernorm_h16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
 

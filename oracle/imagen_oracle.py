@@ -315,6 +315,28 @@ class CrossAttention(nn.Module):
         return self.to_out(out)
 
 
+class LinearCrossAttention(CrossAttention):
+    """imagen_pytorch.LinearCrossAttention: same parameters as CrossAttention; softmax of q over the head dimension and of k over the
+    (null + context) tokens, context = k^T v, out = q context."""
+
+    def forward(self, x, context):
+        b, n, h = x.shape[0], x.shape[1], self.heads
+        x = self.norm(x)
+        q = self.to_q(x)
+        k, v = self.to_kv(context).chunk(2, dim=-1)
+        q, k, v = (t.view(b, t.shape[1], h, -1).transpose(1, 2).reshape(b * h, t.shape[1], -1) for t in (q, k, v))
+        nk, nv = (t.view(1, 1, -1).expand(b * h, 1, -1) for t in self.null_kv.unbind(dim=-2))
+        k = torch.cat((nk, k), dim=-2)
+        v = torch.cat((nv, v), dim=-2)
+        q = q.softmax(dim=-1)
+        k = k.softmax(dim=-2)
+        q = q * self.scale
+        ctx = torch.einsum("b n d, b n e -> b d e", k, v)
+        out = torch.einsum("b n d, b d e -> b n e", q, ctx)
+        out = out.view(b, h, n, -1).transpose(1, 2).reshape(b, n, -1)
+        return self.to_out(out)
+
+
 class Attention(nn.Module):
     """Multi-query self attention: one shared K/V head."""
 
@@ -462,14 +484,15 @@ class LinearAttentionTransformerBlock(nn.Module):
 
 
 class ResnetBlock(nn.Module):
-    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, use_gca=False, **attn_kwargs):
+    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, linear_attn=False, use_gca=False, **attn_kwargs):
         super().__init__()
         self.time_mlp = None
         if exists(time_cond_dim):
             self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_cond_dim, dim_out * 2))
         self.cross_attn = None
         if exists(cond_dim):
-            self.cross_attn = EinopsToAndFrom(CrossAttention(dim=dim_out, context_dim=cond_dim, **attn_kwargs))
+            attn_klass = CrossAttention if not linear_attn else LinearCrossAttention
+            self.cross_attn = EinopsToAndFrom(attn_klass(dim=dim_out, context_dim=cond_dim, **attn_kwargs))
         self.block1 = Block(dim, dim_out, groups=groups)
         self.block2 = Block(dim_out, dim_out, groups=groups)
         self.gca = GlobalContext(dim_in=dim_out, dim_out=dim_out) if use_gca else Always(1)
@@ -583,7 +606,7 @@ class Unet(nn.Module):
         init_dim=None, resnet_groups=8, init_cross_embed_kernel_sizes=(3, 7, 15), attn_pool_text=True,
         attn_pool_num_latents=32, memory_efficient=False, init_conv_to_final_conv_residual=False,
         use_global_context_attn=True, scale_skip_connection=True, final_resnet_block=True, final_conv_kernel_size=3,
-        use_linear_attn=False,
+        use_linear_attn=False, use_linear_cross_attn=False,
     ):
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
@@ -648,11 +671,12 @@ class Unet(nn.Module):
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
         use_linear_attn = cast_tuple(use_linear_attn, num_layers)
-        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns, use_linear_attn]
+        use_linear_cross_attn = cast_tuple(use_linear_cross_attn, num_layers)
+        layer_params = [num_resnet_blocks, resnet_groups, layer_attns, layer_attns_depth, layer_cross_attns, use_linear_attn, use_linear_cross_attn]
         reversed_layer_params = [tuple(reversed(p)) for p in layer_params]
         skip_connect_dims = []
 
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(zip(in_out, *layer_params)):
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin, layer_lin_cross) in enumerate(zip(in_out, *layer_params)):
             is_last = ind >= (num_layers - 1)
             layer_cond_dim = cond_dim if layer_cross_attn else None
             current_dim = dim_in
@@ -671,7 +695,7 @@ class Unet(nn.Module):
                 nn.ModuleList(
                     [
                         pre_downsample,
-                        ResnetBlock(current_dim, current_dim, cond_dim=layer_cond_dim, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
+                        ResnetBlock(current_dim, current_dim, cond_dim=layer_cond_dim, linear_attn=layer_lin_cross, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
                         nn.ModuleList(
                             [ResnetBlock(current_dim, current_dim, time_cond_dim=time_cond_dim, groups=groups, use_gca=use_global_context_attn)
                              for _ in range(n_blocks)]
@@ -689,7 +713,7 @@ class Unet(nn.Module):
         self.mid_attn = TransformerBlock(mid_dim, depth=layer_mid_attns_depth, **attn_kwargs) if attend_at_middle else None
         self.mid_block2 = ResnetBlock(mid_dim, mid_dim, cond_dim=cond_dim, time_cond_dim=time_cond_dim, groups=resnet_groups[-1], **attn_kwargs)
 
-        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin) in enumerate(
+        for ind, ((dim_in, dim_out), n_blocks, groups, layer_attn, attn_depth, layer_cross_attn, layer_lin, layer_lin_cross) in enumerate(
             zip(reversed(in_out), *reversed_layer_params)
         ):
             is_last = ind == (len(in_out) - 1)
@@ -698,7 +722,7 @@ class Unet(nn.Module):
             self.ups.append(
                 nn.ModuleList(
                     [
-                        ResnetBlock(dim_out + skip_connect_dim, dim_out, cond_dim=layer_cond_dim, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
+                        ResnetBlock(dim_out + skip_connect_dim, dim_out, cond_dim=layer_cond_dim, linear_attn=layer_lin_cross, time_cond_dim=time_cond_dim, groups=groups, **attn_kwargs),
                         nn.ModuleList(
                             [ResnetBlock(dim_out + skip_connect_dim, dim_out, time_cond_dim=time_cond_dim, groups=groups, use_gca=use_global_context_attn)
                              for _ in range(n_blocks)]

@@ -915,3 +915,34 @@ def test_attn_mqa_tcgen05_matches_mma_sync_kernel(cuda_lib, B, N, Jc):
     if B > 1:
         one = ops.attn_mqa(dq[1:2].contiguous(), kv[1:2].contiguous(), heads, d ** -0.5)
         assert torch.equal(one[0], out_tc[1])
+
+
+@pytest.mark.parametrize("B,N,J", [(2, 256, 4), (1, 1000, 38)])
+def test_linear_cross_attention_matches_oracle(cuda_lib, B, N, J):
+    """LinearCrossAttention.forward (Unet(use_linear_cross_attn=...)): keys / values are the null + context tokens only."""
+    from kidney_diffusion_b200 import ops
+    from oracle.imagen_oracle import LinearCrossAttention
+
+    torch.manual_seed(N + J)
+    dim, cd, heads = 128, 96, 8
+    mod = LinearCrossAttention(dim, context_dim=cd, dim_head=64, heads=heads).eval()
+    with torch.no_grad():
+        mod.to_q.weight.copy_(rb(mod.to_q.weight * 3.0))
+        mod.to_out[0].weight.copy_(rb(mod.to_out[0].weight))
+    x = rb(torch.randn(B, N, dim))
+    ctx = torch.randn(B, J, cd)
+    with torch.no_grad():
+        ref = mod(x, ctx)
+    dx = bf(x).to(DEV).view(B, N, 1, dim)
+    xn = ops.layernorm_h16(dx, mod.norm.g.detach().to(DEV))
+    q = ops.conv_gemm(xn, bf(mod.to_q.weight.detach()).to(DEV), None, ksize=1).view(B, N, -1)
+    kv = ops.linear_small(ctx.to(DEV).view(B * J, cd), mod.to_kv.weight.detach().to(DEV)).view(B, J, -1)
+    nk = mod.null_kv.detach().to(DEV)
+    null_row = torch.cat((nk[0].repeat(heads), nk[1].repeat(heads))).view(1, 1, -1).expand(B, 1, -1)
+    tokens = torch.cat((null_row, kv), 1).contiguous()
+    o = ops.linear_attention(q, heads, mod.scale, tokens, act=ops.ACT_NONE, pixels_kv=False)
+    o = ops.conv_gemm(o.view(B, N, 1, -1), bf(mod.to_out[0].weight.detach()).to(DEV), None, ksize=1)
+    out = ops.layernorm_h16(o, mod.to_out[1].g.detach().to(DEV)).view(B, N, dim)
+    err = rel_l2(out, ref)
+    print(f"linear cross attention N={N} J={J}: rel_l2 = {err:.3e}")
+    assert err < 5e-3

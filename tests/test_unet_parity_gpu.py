@@ -24,7 +24,8 @@ def _report(taps_dev, taps_ref):
     ("u2", U2_KW, True, 64, 2),
     ("u1", U1_KW, False, 32, 3),
     ("u3_b1_rect", U3_KW, True, 64, 1),
-    ("u1_linear_attn", dict(U1_KW, layer_attns=(False, False, True, True), use_linear_attn=(False, True, False, False)), False, 32, 2),
+    ("u1_linear_attn", dict(U1_KW, layer_attns=(False, False, True, True), use_linear_attn=(False, True, False, False),
+                            use_linear_cross_attn=(False, True, False, False)), False, 32, 2),
 ])
 def test_unet_forward_parity(cuda_lib, name, kw, lowres, S, B):
     ou, pu = make_pair(kw, lowres_cond=lowres, seed=sum(map(ord, name)))
