@@ -210,7 +210,7 @@ __device__ __forceinline__ float gca_logit(const float* __restrict__ lg, long p,
 }
 
 __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restrict__ logits, int n_parts, long part_stride, long HW,
-                                int C, int nblk, float* __restrict__ part, float* __restrict__ ml) {
+                                int C, int nblk, float* __restrict__ part, float* __restrict__ ml, int e_cache) {
   kd_pdl_wait();  // programmatic dependent launch: this grid may have been scheduled while its stream predecessor drains
   kd_pdl_trigger();
   extern __shared__ float sm[];  // max(T, lanes*C) floats
@@ -226,9 +226,18 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
   const long p0 = (long)blockIdx.x * per;
   const long p1 = p0 + per < HW ? p0 + per : HW;
   const float* lg = logits + (long)b * HW;
+  // The softmax weight of a pixel is the same for all of its C / 8 octet threads: with the chunk's logits cached in shared memory
+  // (e_cache floats behind the reduction scratch) each pixel's n_parts partial logits are summed and exponentiated ONCE per block
+  // instead of once per octet thread (C = 1024: 128 threads x 16 loads + 1 exp per pixel made the kernel instruction-bound).
+  float* s_e = sm + (size_t)T * 8;
+  const bool cached = (p1 - p0) <= (long)e_cache;
   // block max of the chunk's logits
   float m = -INFINITY;
-  for (long p = p0 + threadIdx.x; p < p1; p += T) m = fmaxf(m, gca_logit(lg, p, n_parts, part_stride));
+  for (long p = p0 + threadIdx.x; p < p1; p += T) {
+    const float v = gca_logit(lg, p, n_parts, part_stride);
+    if (cached) s_e[p - p0] = v;
+    m = fmaxf(m, v);
+  }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -239,6 +248,10 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
   }
   __syncthreads();
   m = s_m;
+  if (cached) {
+    for (long p = p0 + threadIdx.x; p < p1; p += T) s_e[p - p0] = __expf(s_e[p - p0] - m);
+    __syncthreads();
+  }
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float l = 0.f;
   const h16* xb = x + (long)b * HW * C + (long)o * 8;
@@ -246,15 +259,15 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
   // four pixels per step, loads first (memory-level parallelism); accumulation order per thread is unchanged
   for (; p + 3L * lanes < p1; p += 4L * lanes) {
     int4 raw[4];
-    float lgv[4];
+    float ev[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       raw[u] = ld_stream(xb + (p + (long)u * lanes) * C);
-      lgv[u] = gca_logit(lg, p + (long)u * lanes, n_parts, part_stride);
+      ev[u] = cached ? s_e[p + (long)u * lanes - p0] : __expf(gca_logit(lg, p + (long)u * lanes, n_parts, part_stride) - m);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float e = __expf(lgv[u] - m);
+      const float e = ev[u];
       float v[8];
       h16x8_to_float(*reinterpret_cast<h16x8*>(&raw[u]), v);
 #pragma unroll
@@ -263,7 +276,7 @@ __global__ void gca_pool_kernel(const h16* __restrict__ x, const float* __restri
     }
   }
   for (; p < p1; p += lanes) {
-    const float e = __expf(gca_logit(lg, p, n_parts, part_stride) - m);
+    const float e = cached ? s_e[p - p0] : __expf(gca_logit(lg, p, n_parts, part_stride) - m);
     int4 raw = ld_stream(xb + p * C);
     float v[8];
     h16x8_to_float(*reinterpret_cast<h16x8*>(&raw), v);
@@ -968,8 +981,10 @@ extern "C" int kd_gca_pool(const void* x, const float* logits, int n_parts, int 
   KD_REQUIRE(x && logits && part && ml && B > 0 && HW > 0 && nblk > 0 && n_parts >= 1, "kd_gca_pool: bad argument");
   KD_CHECK_OCT(C);
   const int T = threads_for_oct(C / 8);
-  const size_t smem = sizeof(float) * (size_t)T * 8;
-  KD_CUDA(kd_launch(gca_pool_kernel, dim3(nblk, B), dim3(T), smem, stream, reinterpret_cast<const h16*>(x), logits, n_parts, (long)B * HW, HW, C, nblk, part, ml));
+  const long per = (HW + nblk - 1) / nblk;
+  const int e_cache = per <= 8192 ? (int)per : 0;  // chunk logits cached in shared memory (<= 32 KB)
+  const size_t smem = sizeof(float) * ((size_t)T * 8 + e_cache);
+  KD_CUDA(kd_launch(gca_pool_kernel, dim3(nblk, B), dim3(T), smem, stream, reinterpret_cast<const h16*>(x), logits, n_parts, (long)B * HW, HW, C, nblk, part, ml, e_cache));
   return KD_OK;
 }
 
