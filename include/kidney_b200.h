@@ -250,16 +250,6 @@ int kd_final_conv(const void* xa /* fp16 [B,H,W,Ca] */, int Ca, const float* xb 
                   const float* w /* fp32 [Cout][3][3][Ca+Cb] */, const void* w_split, const float* bias,
                   float* out /* fp32 NCHW [B,Cout,H,W] */, int B, int H, int W, int Cout, kd_stream_t stream);
 
-/* Unet.final_conv on the 5th-gen tensor cores (csrc/kd_final_conv_tc.cu): 16 x 8 pixel tiles, the 18 x 10 halo of a 64-channel chunk
- * by one TMA box, the hi / lo split filter as a 16-row UMMA operand resident in shared memory, 16 fp32 accumulator columns in TMEM.
- * Used when kd_final_conv_tc_supported (Ca % 64 == 0, Ca <= 256, Cb <= 4, Cout <= 4, H >= 16, W >= 8); w_packed:
- * kd_final_conv_tc_pack_elems(Ca) fp16 elements written once per model by kd_final_conv_tc_pack. */
-long kd_final_conv_tc_pack_elems(int Ca);
-int kd_final_conv_tc_supported(int Ca, int Cb, int Cout, int H, int W);
-int kd_final_conv_tc_pack(const float* w /* fp32 [Cout][3][3][Ca+Cb] */, int Cout, int Ca, int Cb, void* w_packed, kd_stream_t stream);
-int kd_final_conv_tc(const void* xa, int Ca, const float* xb, int Cb, const void* w_packed, const float* bias, float* out, int B, int H, int W,
-                     int Cout, kd_stream_t stream);
-
 /* ------------------------------------------------------------------ K6 / K7: sampler update
  * replaces: Imagen.p_mean_variance + p_sample (x0 from eps / v, dynamic threshold = torch.quantile(|x0|, 0.95) per sample,
  *           clamp(min=1), q_posterior mean, ancestral noise), the RePaint blend / re-noise of p_sample_loop and the

@@ -75,10 +75,6 @@ SIGNATURES = {
     "kd_final_conv_pack_elems": (c_long, [_I]),
     "kd_final_conv_pack": (c_int, [_P, _I, _I, _I, _P, _P]),
     "kd_final_conv": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "kd_final_conv_tc_pack_elems": (c_long, [_I]),
-    "kd_final_conv_tc_supported": (c_int, [_I, _I, _I, _I, _I]),
-    "kd_final_conv_tc_pack": (c_int, [_P, _I, _I, _I, _P, _P]),
-    "kd_final_conv_tc": (c_int, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "kd_dynthresh_workspace_bytes": (c_size_t, [_I]),
     "kd_dynthresh": (c_int, [_P, _P, _I, _L, _I, _F, _F, _L, _L, _F, _P, c_size_t, _P, _P]),
     "kd_ddpm_step": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _I, _F, _F, _F, _F, _F, _F, _P, _F, _F, _F, _P]),

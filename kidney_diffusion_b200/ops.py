@@ -624,9 +624,6 @@ def init_conv(x, ksize, w_packed, bias, addend, out, algo_taps=None):
     return out
 
 
-FINAL_CONV_TC = True  # tcgen05 final conv where the shape allows (False: the mma.sync kernel everywhere; tests)
-
-
 @_timed
 def final_conv(xa, xb, w, bias):
     """xa: NHWC fp16; xb: NCHW fp32 or None; w: fp32 [Cout,3,3,Ca+Cb] -> NCHW fp32 [B,Cout,H,W]."""
@@ -635,15 +632,6 @@ def final_conv(xa, xb, w, bias):
     Cb = 0 if xb is None else xb.shape[1]
     Cout = w.shape[0]
     out = torch.empty((B, Cout, H, W), device=xa.device, dtype=torch.float32)
-    if FINAL_CONV_TC and lib().kd_final_conv_tc_supported(Ca, Cb, Cout, H, W):  # tcgen05 kernel (choice by shape only)
-        wt = getattr(w, "_kd_split_tc", None)
-        if wt is None:
-            wt = torch.empty((lib().kd_final_conv_tc_pack_elems(Ca),), device=xa.device, dtype=ACT_DTYPE)
-            check(lib().kd_final_conv_tc_pack(_ptr(w), Cout, Ca, Cb, _ptr(wt), _stream()), "kd_final_conv_tc_pack")
-            w._kd_split_tc = wt
-        check(lib().kd_final_conv_tc(_ptr(xa), Ca, _ptr(xb), Cb, _ptr(wt), _ptr(bias), _ptr(out), B, H, W, Cout, _stream()), "kd_final_conv_tc")
-        _count()
-        return out
     ws = getattr(w, "_kd_split", None)
     if ws is None:  # one-time hi + lo fp16 split of the filter (cached on the weight tensor)
         ws = torch.empty((lib().kd_final_conv_pack_elems(Ca),), device=xa.device, dtype=ACT_DTYPE)

@@ -1,3 +1,9 @@
+// EXPERIMENT (not part of libkidney_b200.so): tcgen05 formulation of Unet.final_conv.  Correct (rel-L2 < 1e-5 vs F.conv2d on five
+// shapes, batch-invariant) but 1.8x SLOWER than the shipped mma.sync kernel: 3.0 ms vs 1.67 ms at B = 8, 1024^2.  Every N = 16 MMA
+// costs ~140 cycles regardless of how many independent TMEM accumulators are used (1 or 8: same time), i.e. a per-instruction floor
+// of the tensor pipe for M = 128 operands, not a dependency chain: 72 MMAs per 128-pixel tile = 10 000 cycles against 1 600 cycles
+// of HBM time.  The same floor (~105 cycles per MMA) is what holds the Cout = 128 convolutions at 0.66 of cuBLAS's duty cycle
+// (profiles/README.md, round 2, item 9).  Kept for the record; it would need cta_group::2 (M = 256 per instruction) to break even.
 // Unet.final_conv (3x3, Cout <= 4 output channels) on cat(x [NHWC fp16, Ca channels], lowres_cond_img [NCHW fp32, Cb <= 4]) as a
 // tcgen05 kernel: the op is HBM-bound (one read of the 128-channel activation, 268 MB per 1024^2 image), so the design goal is to
 // stream halo tiles at memory speed with as few issue slots as possible -- which the mma.sync version (N = 8 fragments through
@@ -24,6 +30,9 @@ constexpr int FT_AS = 4;                                                   // ha
 constexpr int FT_WBLK = 16 * 128;                                          // one (chunk, tap) filter block: 16 rows x 64 k
 constexpr int FT_THREADS = 192;                                            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int FT_MAXC = 4;
+constexpr int FT_NACC = 8;   // independent accumulators per tile (16 TMEM columns each), used round-robin by the (chunk, tap) MMAs: a chain of
+                             // dependent N = 16 MMAs into ONE accumulator is latency-bound (~140 cycles each); the epilogue adds them up
+constexpr int FT_TCOLS = 2 * FT_NACC * 16;  // two accumulator stages
 
 struct FinalParams {
   const float* xb;    // [B, Cb, H, W] fp32 or null
@@ -74,7 +83,7 @@ final_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 32);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), FT_TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -112,7 +121,7 @@ final_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
       mbar_wait(smem_u32(&t_empty[as]), aph ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 16;
+      const uint32_t d_tmem = tmem_base + as * (FT_NACC * 16);
       for (int ch = 0; ch < chunks; ++ch, ++it) {
         const uint32_t s = it % FT_AS, ph = (it / FT_AS) & 1u;
         mbar_wait(smem_u32(&a_full[s]), ph);
@@ -125,7 +134,11 @@ final_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const uint64_t a_desc = make_sw128_desc(a_stage + (uint32_t)(ky * FT_HW + kx) * 128u, FT_HW * 128);
             const uint64_t b_desc = make_sw128_desc(w_s + (uint32_t)(ch * 9 + tap) * FT_WBLK);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC, (ch | tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const int seq = (ch * 9 + tap) * 4 + k;  // accumulator seq % FT_NACC; its first use overwrites, later uses accumulate
+              umma_f16(d_tmem + (uint32_t)(seq % FT_NACC) * 16u, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC,
+                       seq >= FT_NACC ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&a_empty[s]));
         }
@@ -162,9 +175,20 @@ final_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
       mbar_wait_relaxed(smem_u32(&t_full[as]), aph);
       tc_fence_after();
-      uint32_t acc[16];
-      tmem_ld16(tmem_base + as * 16 + ((uint32_t)(quarter * 32) << 16), acc);
-      tmem_ld_wait();
+      float sum[2 * FT_MAXC];
+#pragma unroll
+      for (int j = 0; j < 2 * FT_MAXC; ++j) sum[j] = 0.f;
+#pragma unroll
+      for (int a = 0; a < FT_NACC; a += 2) {  // fixed order: the result does not depend on timing
+        uint32_t acc[2][16];
+        tmem_ld16(tmem_base + as * (FT_NACC * 16) + (uint32_t)a * 16u + ((uint32_t)(quarter * 32) << 16), acc[0]);
+        tmem_ld16(tmem_base + as * (FT_NACC * 16) + (uint32_t)(a + 1) * 16u + ((uint32_t)(quarter * 32) << 16), acc[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int j = 0; j < 2 * FT_MAXC; ++j) sum[j] += __uint_as_float(acc[u][j]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&t_empty[as]));
@@ -173,7 +197,7 @@ final_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int co = 0; co < FT_MAXC; ++co)
           if (co < p.Cout)
             p.out[(((long)b * p.Cout + co) * p.H + h) * p.W + w] =
-                (__uint_as_float(acc[co]) + __uint_as_float(acc[FT_MAXC + co])) + extra[co] + s_bias[co];
+                (sum[co] + sum[FT_MAXC + co]) + extra[co] + s_bias[co];
       }
     }
   }
@@ -181,7 +205,7 @@ final_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 32);
+    tmem_dealloc(tmem_base, FT_TCOLS);
   }
 }
 

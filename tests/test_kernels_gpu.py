@@ -946,32 +946,3 @@ def test_linear_cross_attention_matches_oracle(cuda_lib, B, N, J):
     err = rel_l2(out, ref)
     print(f"linear cross attention N={N} J={J}: rel_l2 = {err:.3e}")
     assert err < 5e-3
-
-
-@pytest.mark.parametrize("B,H,W,Ca,Cb,Cout", [(2, 40, 72, 128, 3, 3), (1, 128, 128, 128, 3, 3), (3, 16, 8, 64, 0, 3), (1, 50, 30, 256, 4, 4), (2, 64, 64, 128, 0, 1)])
-def test_final_conv_tcgen05_matches_conv2d_and_legacy(cuda_lib, B, H, W, Ca, Cb, Cout):
-    """kd_final_conv_tc (tcgen05, halo TMA box, hi / lo split filter) against F.conv2d in fp32 and the mma.sync kernel: ragged tiles
-    (H, W not multiples of 16 / 8), 1-4 output channels, with and without the fp32 low-res channels; batch invariance."""
-    from kidney_diffusion_b200 import ops
-
-    g = torch.Generator().manual_seed(H * W + Ca + Cb)
-    xa = rb(torch.randn(B, Ca, H, W, generator=g))
-    xb = torch.randn(B, Cb, H, W, generator=g) if Cb else None
-    w, b = torch.randn(Cout, Ca + Cb, 3, 3, generator=g) * 0.05, torch.randn(Cout, generator=g)
-    ref = F.conv2d(xa if xb is None else torch.cat((xa, xb), 1), w, b, padding=1)
-    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV)
-    dxa, dxb = nhwc(xa), None if xb is None else xb.to(DEV)
-    assert ops.lib().kd_final_conv_tc_supported(Ca, Cb, Cout, H, W) == 1
-    out = ops.final_conv(dxa, dxb, wd, b.to(DEV))
-    try:
-        ops.FINAL_CONV_TC = False
-        legacy = ops.final_conv(dxa, dxb, w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV))
-    finally:
-        ops.FINAL_CONV_TC = True
-    torch.cuda.synchronize()
-    err, err_l = rel_l2(out, ref), rel_l2(legacy, ref)
-    print(f"final conv {B}x{H}x{W} {Ca}+{Cb}->{Cout}: tcgen05 {err:.2e}, mma.sync {err_l:.2e}")
-    assert out.shape == ref.shape and bool(torch.isfinite(out).all()) and err < 1e-5
-    if B > 1:
-        one = ops.final_conv(dxa[1:2].contiguous(), None if dxb is None else dxb[1:2].contiguous(), wd, b.to(DEV))
-        assert torch.equal(one[0], out[1])
