@@ -328,6 +328,40 @@ int kd_patch_paste(const float* patch /* fp32 [3,P,P] */, float* canvas, int Wc,
  * Imagen.check_saturation runs it on every stored activation tensor of a sample() call. */
 int kd_count_saturated(const void* x, long n, unsigned long long* counter, kd_stream_t stream);
 
+/* ------------------------------------------------------------------ fp32 ("precise") path (kd_precise.cu)
+ * The reference runs the whole UNet in fp32 (imagen_pytorch/imagen_pytorch.py, Unet.forward; ImagenTrainer(fp16=False) in
+ * train_ultra_res_v_param.py:109-115).  These entry points compute the same operations as the fp16 tensor-core path on fp32 NHWC
+ * activations with fp32 weights and fp32 accumulation on the CUDA cores: the "fp32 path" of BASELINE.json's north_star (parity
+ * 1e-4).  Selected explicitly (Imagen.set_precision("fp32")); 20-50x slower than the tensor-core path.
+ *
+ * kd_conv_f32: Conv2d ksize x ksize / stride / pad over the channel concat [xa (Ca) | xb (Cb)], weights [Cout, ksize*ksize*(Ca+Cb)]
+ * (tap-major, channel-minor); out = act(conv + bias) + addend * addend_scale[b, n]; out_mode 1 stores through PixelShuffle(2)
+ * (conv channel n = (dy*2+dx) * Cout/4 + c).  Downsample's pixel-unshuffle + 1x1 conv is ksize 2 / stride 2 / pad 0. */
+int kd_conv_f32(const float* xa, int Ca, const float* xb, int Cb, const float* w, const float* bias, const float* addend,
+                const float* addend_scale /* [B, Cout] or NULL */, float* out, int B, int Hin, int Win, int Cout, int ksize, int stride,
+                int pad, int act, int out_mode, kd_stream_t stream);
+/* GroupNorm over the concat [xa | scale_b * xb] (Block.forward: groupnorm -> * (scale + 1) + shift -> SiLU): fp64 partial sums per
+ * (sample, group, pixel chunk) -> mean / rstd -> apply.  kd_gn_chunks_f32(HW) chunks per group (a function of HW only). */
+int kd_gn_chunks_f32(long HW);
+int kd_gn_stats_f32(const float* xa, int Ca, const float* xb, int Cb, float scale_b, int B, long HW, int G,
+                    double* partial /* [B, G, kd_gn_chunks_f32(HW), 2] */, kd_stream_t stream);
+int kd_gn_finalize_f32(const double* partial, int B, long HW, int G, int group_size, float eps, float* mean_rstd /* [B, G, 2] */,
+                       kd_stream_t stream);
+int kd_gn_apply_f32(const float* x, float* y, int B, long HW, int C, int c_offset, int group_size, int G, float src_scale,
+                    const float* mean_rstd, const float* gamma, const float* beta, const float* scale_shift /* rows [scale | shift] or NULL */,
+                    long ss_stride, int ctot, int act, kd_stream_t stream);
+/* GlobalContext (to_k logits, softmax over pixels, pooled = softmax @ x, h * gate + residual) */
+int kd_rowdot_f32(const float* x /* [M, C] */, const float* w, const float* bias /* [1] or NULL */, float* out /* [M] */, long M, int C,
+                  kd_stream_t stream);
+int kd_softmax_pool_f32(const float* x /* [B, HW, C] */, const float* logits /* [B, HW] */, int B, long HW, int C, float* ml /* [B, 2] */,
+                        float* part /* [B, kd_gn_chunks_f32(HW), C] */, float* pooled /* [B, C] */, kd_stream_t stream);
+int kd_gate_residual_f32(const float* h, const float* gate /* [B, C] */, const float* res, float* out, int B, long HW, int C, kd_stream_t stream);
+/* Softmax attention with head dim 64: q [B, N, ldq] (head h at column 64 h), key j of head h of sample b at
+ * k + b * k_batch + j * ldk + h * k_head (k_head = 0: one shared K/V head, Attention; 64: per-head, CrossAttention), v likewise;
+ * out [B, N, heads * 64].  Replaces Attention.forward / CrossAttention.forward after their projections. */
+int kd_attn_f32(const float* q, long ldq, const float* k, long ldk, long k_batch, int k_head, const float* v, long ldv, long v_batch, int v_head,
+                float* out, int B, int N, int J, int heads, float scale, kd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,15 @@ SIGNATURES = {
     "kd_linattn_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "kd_linattn_context": (c_int, [_P, _L, _I, _I, _I, _I, _I, _P, _I, _P, c_size_t, _P, _P]),
     "kd_linattn_apply": (c_int, [_P, _L, _I, _P, _P, _I, _I, _I, _F, _I, _P]),
+    "kd_conv_f32": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "kd_gn_chunks_f32": (c_int, [_L]),
+    "kd_gn_stats_f32": (c_int, [_P, _I, _P, _I, _F, _I, _L, _I, _P, _P]),
+    "kd_gn_finalize_f32": (c_int, [_P, _I, _L, _I, _I, _F, _P, _P]),
+    "kd_gn_apply_f32": (c_int, [_P, _P, _I, _L, _I, _I, _I, _I, _F, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "kd_rowdot_f32": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
+    "kd_softmax_pool_f32": (c_int, [_P, _P, _I, _L, _I, _P, _P, _P, _P]),
+    "kd_gate_residual_f32": (c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
+    "kd_attn_f32": (c_int, [_P, _L, _P, _L, _L, _I, _P, _L, _L, _I, _P, _I, _I, _I, _I, _F, _P]),
     "kd_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "kd_peer_free": (c_int, [_P]),
     "kd_peer_export": (c_int, [_P, _P]),

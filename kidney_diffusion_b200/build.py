@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libkidney_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 
 SOURCES = ["kd_abi.cu", "kd_conv_gemm.cu", "kd_norm_gca.cu", "kd_cond_attn.cu", "kd_sampler.cu", "kd_edge_convs.cu", "kd_init_conv.cu",
-           "kd_grid_peer.cu", "kd_guard.cu", "kd_linattn.cu", "kd_attn_tc.cu"]
+           "kd_grid_peer.cu", "kd_guard.cu", "kd_linattn.cu", "kd_attn_tc.cu", "kd_precise.cu"]
 CC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 NVCC_FLAGS = CC_FLAGS + LINK_FLAGS  # (kept for the stamp)

@@ -17,6 +17,10 @@ from .modules import (
 
 
 class Unet(nn.Module):
+    # "fp16": tcgen05 tensor-core path (fp16 storage, fp32 accumulation; per-step rel-L2 <= 1e-2 vs the fp32 reference).
+    # "fp32": precise path (csrc/kd_precise.cu: fp32 storage and CUDA-core accumulation; per-step rel-L2 <= 1e-4), 20-50x slower.
+    precision = "fp16"
+
     def __init__(
         self, *, dim, image_embed_dim=1024, text_embed_dim=768, num_resnet_blocks=1, cond_dim=None, num_image_tokens=4,
         num_time_tokens=2, learned_sinu_pos_emb_dim=16, out_dim=None, dim_mults=(1, 2, 4, 8), cond_images_channels=0, channels=3,
@@ -194,9 +198,9 @@ class Unet(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("kidney_diffusion_b200.Unet runs on a B200 only: move the module to a CUDA device (no CPU fallback)")
-        stamp = (dev, sum(p._version for p in self.parameters()))
+        stamp = (dev, sum(p._version for p in self.parameters()), self.precision)
         if self._executor is None or self._executor.stamp != stamp:
-            self._executor = UnetExecutor(self, dev, stamp)
+            self._executor = UnetExecutor(self, dev, stamp, precision=self.precision)
         return self._executor
 
     def _apply(self, fn, *args, **kwargs):

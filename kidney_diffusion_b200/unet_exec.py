@@ -27,15 +27,18 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import ops, ops_f32
 from .modules import LinearAttentionTransformerBlock, Parallel, PixelShuffleUpsample, TransformerBlock, exists
 
 H16 = ops.ACT_DTYPE  # 16-bit activation / weight dtype (saturating fp16)
 IM2COL_BUDGET_BYTES = 4 << 30
 
 
+_PACK_DTYPE = [H16]  # dtype the packers below produce: fp16 for the tensor-core path, fp32 while a precise executor is being built
+
+
 def _bf(t):
-    return t.detach().to(H16).contiguous()
+    return t.detach().to(_PACK_DTYPE[0]).contiguous()
 
 
 def _pack_conv(weight, b_cols=0, b_scale=1.0):
@@ -134,9 +137,22 @@ def _pack_attn(m):
 
 
 class UnetExecutor:
-    def __init__(self, unet, device, stamp):
-        ops.lib()  # fail loudly if the CUDA library or a B200 is missing
+    def __init__(self, unet, device, stamp, precision="fp16"):
+        """precision "fp16": tensor-core path (fp16 storage, fp32 accumulation).  "fp32": the precise path -- the same forward code
+        over ops_f32 (fp32 weights / storage / FFMA accumulation), without the fused GroupNorm prologue and epilogue statistics."""
+        assert precision in ("fp16", "fp32"), precision
+        self.precise = precision == "fp32"
+        self.K = ops_f32 if self.precise else ops
+        self.adt = torch.float32 if self.precise else H16
+        self.K.lib()  # fail loudly if the CUDA library or a B200 is missing
         self.stamp, self.device, self.u = stamp, device, unet
+        _PACK_DTYPE[0] = self.adt
+        try:
+            self._build(unet, device)
+        finally:
+            _PACK_DTYPE[0] = H16
+
+    def _build(self, unet, device):
         u = unet
         self.skip_scale = u.skip_connect_scale
         self.dim = u.init_conv.convs[0].out_channels + u.init_conv.convs[1].out_channels + u.init_conv.convs[2].out_channels
@@ -166,9 +182,11 @@ class UnetExecutor:
             return _bf(W), Kp
 
         self.init_wx, self.init_kpx = pack_panel_w(x_idx)
+        if self.precise:  # un-padded merged filter, K = (ky, kx, c)
+            self.init_wx = Wm[..., x_idx].reshape(self.dim, -1).contiguous()
 
-        # panel-free path (ops.init_conv): <= 3 image channels per call, K ordered (ky, c, kx padded to 16)
-        self.init_direct = self.dim in (64, 128)
+        # panel-free path (self.K.init_conv): <= 3 image channels per call, K ordered (ky, c, kx padded to 16)
+        self.init_direct = self.dim in (64, 128) and not self.precise
 
         def pack_direct_w(idx):
             groups = []
@@ -176,7 +194,7 @@ class UnetExecutor:
                 sub = idx[g0:g0 + 3]
                 Wd = torch.zeros(self.dim, ks, len(sub), 16, device=device)
                 Wd[..., :ks] = Wm[..., sub].permute(0, 1, 3, 2)  # [n, ky, kx, c] -> [n, ky, c, kx]
-                Kp = ops.init_conv_kp(len(sub), ks)
+                Kp = self.K.init_conv_kp(len(sub), ks)
                 W = torch.zeros(self.dim, Kp, device=device)
                 W[:, :ks * len(sub) * 16] = Wd.reshape(self.dim, -1)
                 groups.append((g0, g0 + len(sub), _bf(W)))
@@ -189,6 +207,8 @@ class UnetExecutor:
         self.n_fixed = len(fixed_idx)
         if self.n_fixed:
             self.init_wf, self.init_kpf = pack_panel_w(fixed_idx)
+            if self.precise:
+                self.init_wf = Wm[..., fixed_idx].reshape(self.dim, -1).contiguous()
             if self.init_direct:
                 self.init_df = pack_direct_w(fixed_idx)
 
@@ -324,57 +344,62 @@ class UnetExecutor:
             assert fixed.shape[1] == self.n_fixed
             S = fixed.shape[-1]
             if "init_base" not in st:
-                st["init_base"] = torch.empty((B, S, S, self.dim), device=fixed.device, dtype=H16)
+                st["init_base"] = torch.empty((B, S, S, self.dim), device=fixed.device, dtype=self.adt)
             self.init_base = st["init_base"]
             self._init_gemm(fixed, self.init_wf, self.init_kpf, None, None, self.init_base, getattr(self, "init_df", None))
 
     def _init_gemm(self, img, w, Kp, bias, addend, out, direct):
         B, _, S, S2 = img.shape
+        if self.precise:
+            self.K.init_conv_nchw(img, self.init_ks, w, bias, addend, out)
+            return
         if self.init_direct:
             # chained <= 3-channel slices: out = conv(slice_0) + bias + addend, then out = conv(slice_i) + out
             for i, (c0, c1, wd) in enumerate(direct):
                 sub = img if (c0 == 0 and c1 == img.shape[1]) else img[:, c0:c1].contiguous()
-                ops.init_conv(sub, self.init_ks, wd, bias if i == 0 else None, addend if i == 0 else out, out,
+                self.K.init_conv(sub, self.init_ks, wd, bias if i == 0 else None, addend if i == 0 else out, out,
                               algo_taps=self.init_algo_k)
             return
         per = S * S2 * Kp * 2
         chunk = max(1, min(B, IM2COL_BUDGET_BYTES // per))
         for b0 in range(0, B, chunk):
             b1 = min(B, b0 + chunk)
-            panel = ops.im2col_nchw(img[b0:b1], self.init_ks, Kp)
-            ops.gemm_rows(panel, w, bias, addend=None if addend is None else addend[b0:b1].view(-1, self.dim),
+            panel = self.K.im2col_nchw(img[b0:b1], self.init_ks, Kp)
+            self.K.gemm_rows(panel, w, bias, addend=None if addend is None else addend[b0:b1].view(-1, self.dim),
                           out=out[b0:b1].view(-1, self.dim), algo_k=self.init_algo_k * img.shape[1])
             del panel
 
     # ------------------------------------------------------------------ blocks
     def _gn(self, xa, xb, b_scale, G, gamma, beta, ss):
         """GroupNorm(+scale/shift)+SiLU over the (virtual) concat [xa | b_scale * xb] -> activated (ya, yb)."""
+        if self.precise:
+            return self.K.groupnorm(xa, xb, b_scale, G, gamma, beta, ss)
         B, H, W, Ca = xa.shape
         Cb = xb.shape[3] if exists(xb) else 0
         C = Ca + Cb
         gs = C // G
         # statistics come fused from the producer kernel (conv epilogue / gate_residual) when it could emit them
-        mr = ops.gn_finalize_oct(ops.stats_of(xa), 1.0, ops.stats_of(xb) if exists(xb) else None, b_scale, gs, G, count=gs * H * W)
+        mr = self.K.gn_finalize_oct(self.K.stats_of(xa), 1.0, self.K.stats_of(xb) if exists(xb) else None, b_scale, gs, G, count=gs * H * W)
         kw = dict(group_size=gs, num_groups=G, scale_shift=ss, ctot=C)
-        ya = ops.gn_apply(xa, mr, gamma, beta, c_offset=0, **kw)
-        yb = ops.gn_apply(xb, mr, gamma, beta, c_offset=Ca, src_scale=b_scale, **kw) if exists(xb) else None
+        ya = self.K.gn_apply(xa, mr, gamma, beta, c_offset=0, **kw)
+        yb = self.K.gn_apply(xb, mr, gamma, beta, c_offset=Ca, src_scale=b_scale, **kw) if exists(xb) else None
         return ya, yb
 
     def _cross_attn(self, P, h, c):
         B, H, W, C = h.shape
         J = c.shape[1]
-        xn = ops.layernorm_h16(h, P["norm_g"])
-        q = ops.conv_gemm(xn, P["wq"], None, ksize=1)
-        kv = ops.linear_small(c.view(B * J, -1), P["wkv"]).view(B, J, -1)
+        xn = self.K.layernorm_h16(h, P["norm_g"])
+        q = self.K.conv_gemm(xn, P["wq"], None, ksize=1)
+        kv = self.K.linear_small(c.view(B * J, -1), P["wkv"]).view(B, J, -1)
         if P["linear"]:  # LinearCrossAttention: softmax_d(q) @ (softmax_tokens(k)^T v) over the null + context tokens
             inner = P["heads"] * 64
             null_row = torch.cat((P["null_kv"][0].float().repeat(P["heads"]), P["null_kv"][1].float().repeat(P["heads"])))  # k | v, every head
             tokens = torch.cat((null_row.view(1, 1, 2 * inner).expand(B, 1, 2 * inner), kv), 1).contiguous()
-            o = ops.linear_attention(q.view(B, H * W, -1), P["heads"], P["scale"], tokens, act=ops.ACT_NONE, pixels_kv=False)
+            o = self.K.linear_attention(q.view(B, H * W, -1), P["heads"], P["scale"], tokens, act=self.K.ACT_NONE, pixels_kv=False)
         else:
-            o = ops.attn_cross(q.view(B, H * W, -1), kv, P["null_kv"], P["heads"], P["scale"])
-        o = ops.conv_gemm(o.view(B, H, W, -1), P["wo"], None, ksize=1)
-        return ops.layernorm_h16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
+            o = self.K.attn_cross(q.view(B, H * W, -1), kv, P["null_kv"], P["heads"], P["scale"])
+        o = self.K.conv_gemm(o.view(B, H, W, -1), P["wo"], None, ksize=1)
+        return self.K.layernorm_h16(o, P["out_g"], residual=h)  # to_out LayerNorm, then "+ h"
 
     def _gn_coef(self, xa, xb, b_scale, G, gamma, beta, ss):
         """Per-channel affine {A, B} of GroupNorm(+scale/shift) over the (virtual) concat [xa | b_scale * xb], for the
@@ -382,7 +407,7 @@ class UnetExecutor:
         B, H, W, Ca = xa.shape
         C = Ca + (xb.shape[3] if exists(xb) else 0)
         gs = C // G
-        _, coef = ops.gn_finalize_oct(ops.stats_of(xa), 1.0, ops.stats_of(xb) if exists(xb) else None, b_scale, gs, G,
+        _, coef = self.K.gn_finalize_oct(self.K.stats_of(xa), 1.0, self.K.stats_of(xb) if exists(xb) else None, b_scale, gs, G,
                                       count=gs * H * W, gamma=gamma, beta=beta, scale_shift=ss, want_coef=True)
         return coef
 
@@ -391,11 +416,11 @@ class UnetExecutor:
         the shape runs on the halo kernel, else by a separate gn_apply pass."""
         B, H, W, Ca = xa.shape
         Cb = xb.shape[3] if exists(xb) else 0
-        if ops.conv_pre_supported(B, H, W, Ca, Cb, w.shape[0]):
+        if self.K.conv_pre_supported(B, H, W, Ca, Cb, w.shape[0]):
             coef = self._gn_coef(xa, xb, b_scale, G, gamma, beta, ss)
-            return ops.conv_gemm(xa, w, bias, xb=xb, ksize=3, pre_coef=coef, **kw)
+            return self.K.conv_gemm(xa, w, bias, xb=xb, ksize=3, pre_coef=coef, **kw)
         ya, yb = self._gn(xa, xb, b_scale, G, gamma, beta, ss)
-        return ops.conv_gemm(ya, w, bias, xb=yb, ksize=3, **kw)
+        return self.K.conv_gemm(ya, w, bias, xb=yb, ksize=3, **kw)
 
     def _resnet(self, P, xa, xb, ss_all, c):
         h = self._norm_conv(xa, xb, P.b_scale, P.G, P.g1, P.be1, None, P.w1, P.b1, want_stats=not exists(P.xattn))
@@ -407,13 +432,13 @@ class UnetExecutor:
             h2 = self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, logit_w=g["wk"])
             logits = getattr(h2, "_kd_logits", None)  # to_k from the conv epilogue (its bias cancels in the softmax)
             if logits is None:
-                logits = ops.rowdot(h2, g["wk"], g["bk"])
-            gate = ops.gca_gate(h2, logits, g["w0"], g["b0"], g["w1"], g["b1"])
+                logits = self.K.rowdot(h2, g["wk"], g["bk"])
+            gate = self.K.gca_gate(h2, logits, g["w0"], g["b0"], g["w1"], g["b1"])
             if exists(P.wr):  # out = res_conv(x) + gate * h2, fused in the 1x1 conv epilogue
-                return ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1, addend=h2, addend_scale=gate, want_stats=True)
-            return ops.gate_residual(h2, gate, xa, want_stats=True)
+                return self.K.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1, addend=h2, addend_scale=gate, want_stats=True)
+            return self.K.gate_residual(h2, gate, xa, want_stats=True)
         if exists(P.wr):
-            r = ops.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1)
+            r = self.K.conv_gemm(xa, P.wr, P.br, xb=xb, ksize=1)
             return self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, addend=r, want_stats=True)
         return self._norm_conv(h, None, 1.0, P.G, P.g2, P.be2, ss, P.w2, P.b2, addend=xa, want_stats=True)
 
@@ -422,20 +447,20 @@ class UnetExecutor:
         B, H, W, C = x.shape
         N = H * W
         for L in P.layers:
-            xn = ops.layernorm_h16(x, L["norm_g"])
-            qkv = ops.dwconv3x3(ops.conv_gemm(xn, L["wqkv1"], None, ksize=1), L["wdw"]).view(B, N, -1)
+            xn = self.K.layernorm_h16(x, L["norm_g"])
+            qkv = self.K.dwconv3x3(self.K.conv_gemm(xn, L["wqkv1"], None, ksize=1), L["wdw"]).view(B, N, -1)
             ctx_kv = None
             if exists(c) and exists(L["ctx"]):
                 J = c.shape[1]
-                cn = ops.layernorm_f32(c.view(B * J, -1), L["ctx"]["ln_w"], L["ctx"]["ln_b"])
-                ctx_kv = ops.linear_small(cn, L["ctx"]["w"], None).view(B, J, -1)
-            o = ops.linear_attention(qkv, L["heads"], L["scale"], ctx_kv)
-            o = ops.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
-            x = ops.layernorm_h16(o, L["out_g"], residual=x)
-            f = ops.layernorm_h16(x, L["ff_g0"])
-            f = ops.conv_gemm(f, L["ff_w1"], None, ksize=1, act=ops.ACT_GELU)
-            f = ops.layernorm_h16(f, L["ff_g1"])
-            x = ops.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
+                cn = self.K.layernorm_f32(c.view(B * J, -1), L["ctx"]["ln_w"], L["ctx"]["ln_b"])
+                ctx_kv = self.K.linear_small(cn, L["ctx"]["w"], None).view(B, J, -1)
+            o = self.K.linear_attention(qkv, L["heads"], L["scale"], ctx_kv)
+            o = self.K.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
+            x = self.K.layernorm_h16(o, L["out_g"], residual=x)
+            f = self.K.layernorm_h16(x, L["ff_g0"])
+            f = self.K.conv_gemm(f, L["ff_w1"], None, ksize=1, act=self.K.ACT_GELU)
+            f = self.K.layernorm_h16(f, L["ff_g1"])
+            x = self.K.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
         return x
 
     def _transformer(self, P, x, c):
@@ -444,21 +469,21 @@ class UnetExecutor:
         B, H, W, C = x.shape
         N = H * W
         for L in P.layers:
-            xn = ops.layernorm_h16(x, L["norm_g"])
-            qkv = ops.conv_gemm(xn, L["wqkv"], None, ksize=1).view(B, N, -1)
+            xn = self.K.layernorm_h16(x, L["norm_g"])
+            qkv = self.K.conv_gemm(xn, L["wqkv"], None, ksize=1).view(B, N, -1)
             ctx_kv = None
             if exists(c) and exists(L["ctx"]):
                 J = c.shape[1]
-                cn = ops.layernorm_f32(c.view(B * J, -1), L["ctx"]["ln_w"], L["ctx"]["ln_b"])
-                ctx_kv = ops.linear_small(cn, L["ctx"]["w"], L["ctx"]["b"]).view(B, J, -1)
-            kv = ops.kv_assemble(qkv, L["heads"] * 64, ctx_kv, L["null_kv"])
-            o = ops.attn_mqa(qkv, kv, L["heads"], L["scale"])
-            o = ops.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
-            x = ops.layernorm_h16(o, L["out_g"], residual=x)
-            f = ops.layernorm_h16(x, L["ff_g0"])
-            f = ops.conv_gemm(f, L["ff_w1"], None, ksize=1, act=ops.ACT_GELU)
-            f = ops.layernorm_h16(f, L["ff_g1"])
-            x = ops.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
+                cn = self.K.layernorm_f32(c.view(B * J, -1), L["ctx"]["ln_w"], L["ctx"]["ln_b"])
+                ctx_kv = self.K.linear_small(cn, L["ctx"]["w"], L["ctx"]["b"]).view(B, J, -1)
+            kv = self.K.kv_assemble(qkv, L["heads"] * 64, ctx_kv, L["null_kv"])
+            o = self.K.attn_mqa(qkv, kv, L["heads"], L["scale"])
+            o = self.K.conv_gemm(o.view(B, H, W, -1), L["wo"], None, ksize=1)
+            x = self.K.layernorm_h16(o, L["out_g"], residual=x)
+            f = self.K.layernorm_h16(x, L["ff_g0"])
+            f = self.K.conv_gemm(f, L["ff_w1"], None, ksize=1, act=self.K.ACT_GELU)
+            f = self.K.layernorm_h16(f, L["ff_g1"])
+            x = self.K.conv_gemm(f, L["ff_w2"], None, ksize=1, addend=x)
         return x
 
     # ------------------------------------------------------------------ forward
@@ -476,26 +501,26 @@ class UnetExecutor:
         J = J_time + (text["tokens"].shape[1] if exists(text) else 0)
         c_raw = torch.empty((B, J, cd), device=dev, dtype=torch.float32)
         c_flat = c_raw.view(B, J * cd)
-        ops.linear_small(ops.sinu_emb(time.float().contiguous(), self.sinu_w), self.th_w, self.th_b, post_act=ops.ACT_SILU,
+        self.K.linear_small(self.K.sinu_emb(time.float().contiguous(), self.sinu_w), self.th_w, self.th_b, post_act=self.K.ACT_SILU,
                          out=hid[:, :Tc], ldy=nT * Tc)
-        ops.linear_small(hid[:, :Tc], self.tok_w, self.tok_b, out=c_flat[:, : u.num_time_tokens * cd], ldy=J * cd)
+        self.K.linear_small(hid[:, :Tc], self.tok_w, self.tok_b, out=c_flat[:, : u.num_time_tokens * cd], ldy=J * cd)
         if self.lowres:
-            ops.linear_small(ops.sinu_emb(lowres_noise_times.float().contiguous(), self.lsinu_w), self.lth_w, self.lth_b,
-                             post_act=ops.ACT_SILU, out=hid[:, Tc:], ldy=nT * Tc)
-            ops.linear_small(hid[:, Tc:], self.ltok_w, self.ltok_b,
+            self.K.linear_small(self.K.sinu_emb(lowres_noise_times.float().contiguous(), self.lsinu_w), self.lth_w, self.lth_b,
+                             post_act=self.K.ACT_SILU, out=hid[:, Tc:], ldy=nT * Tc)
+            self.K.linear_small(hid[:, Tc:], self.ltok_w, self.ltok_b,
                              out=c_flat[:, u.num_time_tokens * cd: 2 * u.num_time_tokens * cd], ldy=J * cd)
         if exists(text):
             c_raw[:, J_time:] = text["tokens"]  # x- and t-independent, prepared once per sample() call
-            t = ops.linear_small(torch.cat((hid, text["hidden_in"]), 1), text["tc_w"], text["tc_b"])
+            t = self.K.linear_small(torch.cat((hid, text["hidden_in"]), 1), text["tc_w"], text["tc_b"])
         else:
-            t = ops.linear_small(hid, self.tc_w, self.tc_b)
-        c = ops.layernorm_f32(c_raw, self.nc_w, self.nc_b)
-        ss_all = ops.linear_small(t, self.ss_w, self.ss_b, pre_act=ops.ACT_SILU)
+            t = self.K.linear_small(hid, self.tc_w, self.tc_b)
+        c = self.K.layernorm_f32(c_raw, self.nc_w, self.nc_b)
+        ss_all = self.K.linear_small(t, self.ss_w, self.ss_b, pre_act=self.K.ACT_SILU)
         if taps is not None:
             taps["t"], taps["c"] = t, c
 
         # --- init conv (per-step part: the 3 image channels of x; fixed part added in the epilogue)
-        h = torch.empty((B, S, S2, self.dim), device=dev, dtype=H16)
+        h = torch.empty((B, S, S2, self.dim), device=dev, dtype=self.adt)
         self._init_gemm(x, self.init_wx, self.init_kpx, self.init_bias, self.init_base, h, getattr(self, "init_dx", None))
         if taps is not None:
             taps["init_conv"] = h
@@ -508,7 +533,7 @@ class UnetExecutor:
         hiddens = []
         for li, d in enumerate(self.downs):
             if exists(d["pre"]):
-                h = ops.conv_gemm(h, d["pre"][0], d["pre"][1], mode=1, want_stats=True)
+                h = self.K.conv_gemm(h, d["pre"][0], d["pre"][1], mode=1, want_stats=True)
             h = self._resnet(d["init"], h, None, ss_all, c)
             for P in d["blocks"]:
                 h = self._resnet(P, h, None, ss_all, None)
@@ -517,9 +542,9 @@ class UnetExecutor:
                 h = self._transformer(d["attn"], h, c)
             hiddens.append(h)
             if exists(d["post"]):
-                h = ops.conv_gemm(h, d["post"][0], d["post"][1], mode=1, want_stats=True)
+                h = self.K.conv_gemm(h, d["post"][0], d["post"][1], mode=1, want_stats=True)
             elif exists(d["post_parallel"]):
-                h = ops.conv_gemm(h, d["post_parallel"][0], d["post_parallel"][1], ksize=3, want_stats=True)
+                h = self.K.conv_gemm(h, d["post_parallel"][0], d["post_parallel"][1], ksize=3, want_stats=True)
             if taps is not None:
                 taps[f"down{li}"] = h
 
@@ -541,11 +566,11 @@ class UnetExecutor:
             if exists(d["attn"]):
                 h = self._transformer(d["attn"], h, c)
             if exists(d["up"]):
-                h = ops.conv_gemm(h, d["up"][0], d["up"][1], ksize=1, act=ops.ACT_SILU, out_mode=1)
+                h = self.K.conv_gemm(h, d["up"][0], d["up"][1], ksize=1, act=self.K.ACT_SILU, out_mode=1)
             if taps is not None:
                 taps[f"up{li}"] = h
 
         h = self._resnet(self.final_res, h, init_residual, ss_all, None)
         if taps is not None:
             taps["final_res_block"] = h
-        return ops.final_conv(h, self.lowres_img, self.final_w, self.final_b)
+        return self.K.final_conv(h, self.lowres_img, self.final_w, self.final_b)
