@@ -210,7 +210,7 @@ def set_steps(grid, dev, args, steps):
 
 
 def measure_step_table(c, grid, args, sizes):
-    """ms per sampling step of a batch of B patches for every (stage, B) a plan uses: 2 warm-up + 3 timed inner iterations
+    """ms per sampling step of a batch of B patches for every (stage, B) a plan uses: 2 warm-up + 3 timed inner iterations (median)
     of the real StageRun (graph replay + dynamic threshold + update), CUDA events.  Rank 0's numbers are broadcast so that every
     rank plans with the same table."""
     import torch
@@ -234,14 +234,14 @@ def measure_step_table(c, grid, args, sizes):
                                inpaint_images=torch.rand(B, 3, S, S, device=c.dev), inpaint_masks=mask, inpaint_resample_times=1)
             for k in range(2):
                 run.step(k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             torch.cuda.synchronize()
-            e0.record()
+            ev[0].record()
             for k in range(2, 5):
                 run.step(k)
-            e1.record()
+                ev[k - 1].record()
             torch.cuda.synchronize()
-            table[u][B] = e0.elapsed_time(e1) / 3
+            table[u][B] = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(3))  # median: one hiccup must not bend the plan
             del run, cond, lowres
         im.noise_schedulers[u - 1].num_timesteps = saved
     if c.world > 1:
@@ -431,6 +431,30 @@ def run_b200(args):
         unet_tflops = B * UNET3_GFLOP_PER_SAMPLE_1024 * (S / 1024) ** 2 / 1e3 / (ms_per_step / 1e3)
         del run
 
+        # ---------------- live parity at the bench shape: the same patch through the tensor-core path and through the fp32
+        # CUDA-core path (csrc/kd_precise.cu, 1e-6 against the fp32 oracle in tests/test_precise_gpu.py); outside every timed region
+        unet = imagen.unets[2]
+        gp = torch.Generator().manual_seed(7)
+        xp = torch.randn(1, 3, S, S, generator=gp).to(dev)
+        tp, ltp = torch.tensor([0.9], device=dev), torch.full((1,), float(schedule.log_snr("linear", 0.2)), device=dev)
+        kwp = dict(lowres_cond_img=lowres[:1].contiguous(), lowres_noise_times=ltp, cond_images=cond_dev[:1].contiguous())
+        fast = unet(xp, tp, **kwp).clone()
+        unet.precision = "fp32"
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ref32 = unet(xp, tp, **kwp)
+        torch.cuda.synchronize()
+        fp32_s = time.time() - t0
+        unet.precision = "fp16"
+        rn = float(ref32.double().norm().item())
+        parity = dict(rel_l2_fp16_path_vs_fp32_path=float((fast.double() - ref32.double()).norm().item()) / rn if rn > 0 else None, tolerance=1e-2,
+                      what=f"UNet output of one {S}x{S} patch (B = 1), identical inputs; the fp32 path is itself within 1e-4 of the CPU oracle "
+                           "(tests/test_precise_gpu.py, tests/test_unet_parity_gpu.py at 1024^2)", fp32_path_seconds=fp32_s)
+        del fast, ref32, xp
+        unet._executor = None
+        imagen._graphs.clear()
+        torch.cuda.empty_cache()
+
         # ---------------- end to end through the public API: host buffers in, host buffer out, every step
         imagen.noise_schedulers[2].num_timesteps = 1  # one sample() call == one patch-step on the batch (plus the per-call conditioning work)
 
@@ -460,7 +484,7 @@ def run_b200(args):
                                 l2="inputs larger than L2 (activations >= 0.27 GB per tensor per patch)", state_dtype="f32",
                                 unet_gflop_per_patch_step=UNET3_GFLOP_PER_SAMPLE_1024 * (S / 1024) ** 2),
                     roofline=roofline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks, unet_algorithmic_tflops=unet_tflops,
-                    tensor_frac_whole_step=unet_tflops / peaks["tf_sustained"], output=dict(finite=out_ok, checksum=out_sum))
+                    tensor_frac_whole_step=unet_tflops / peaks["tf_sustained"], output=dict(finite=out_ok, checksum=out_sum), parity=parity)
     else:
         # ---------------- N > 1: the 1024^2 stage of the real 21 x 21 wavefront grid
         n_side = args.grid

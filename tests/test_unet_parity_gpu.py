@@ -280,6 +280,16 @@ def test_full_width_u3_forward_parity_at_1024(cuda_lib):
     err = rel_l2(out, ref)
     print(f"[full-width u3 @1024, B=1] unet output rel_l2 = {err:.3e}")
     assert bool(torch.isfinite(out).all()) and err < TOL
+    # the fp32 path at the bench shape: 1e-4 against the oracle, and the GPU-side reference the bench line's parity figure uses
+    import time
+
+    pu.precision = "fp32"
+    t0 = time.time()
+    out32 = pu(x.cuda(), t.cuda(), lowres_cond_img=lr.cuda(), lowres_noise_times=lt.cuda(), cond_images=cond.cuda())
+    torch.cuda.synchronize()
+    e32 = rel_l2(out32, ref)
+    print(f"[full-width u3 @1024, B=1] fp32 path rel_l2 = {e32:.3e} ({time.time() - t0:.1f} s); fp16 vs fp32 path {rel_l2(out, out32):.3e}")
+    assert e32 < 1e-4
 
 
 def test_batch_of_16_at_1024_is_bit_identical_to_single_patches(cuda_lib):
