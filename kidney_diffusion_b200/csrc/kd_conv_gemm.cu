@@ -1216,10 +1216,24 @@ __global__ void __launch_bounds__(128) splitk_finish_kernel(const ConvParams p, 
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
     const float* src = p.splitk_ws + ((size_t)tile * BM + r) * BN + col0 + o * 8;
     const size_t split_stride = (size_t)tiles_total * BM * BN;
-    for (int sp = 0; sp < S; ++sp) {  // fixed order: the result does not depend on how many CTAs ran concurrently
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride) + 1);
-      v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+    // fixed order: the result does not depend on how many CTAs ran concurrently.  Eight splits' loads are issued before the
+    // first add: with one dependent load per add the kernel sat at S x 8 rows L2 round trips (22 us for a 64-pixel image).
+    for (int sp0 = 0; sp0 < S; sp0 += 8) {
+      float4 a0[8], a1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (sp0 + u < S) {
+          a0[u] = __ldg(reinterpret_cast<const float4*>(src + (sp0 + u) * split_stride));
+          a1[u] = __ldg(reinterpret_cast<const float4*>(src + (sp0 + u) * split_stride) + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (sp0 + u < S) {
+          v[0] += a0[u].x; v[1] += a0[u].y; v[2] += a0[u].z; v[3] += a0[u].w;
+          v[4] += a1[u].x; v[5] += a1[u].y; v[6] += a1[u].z; v[7] += a1[u].w;
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += bias8[j];
@@ -1406,7 +1420,9 @@ void choose_split(const KdConvDesc* d, Tiling* t) {
   const long hw = (long)d->H * d->W;
   static int tgt_small = -1, tgt_mid = -1;  // k-blocks per split for <= 8x8 / <= 16x16 images (KD_SPLITK_TARGETS="a,b": tuning hook; 0 = off)
   if (tgt_small < 0) {
-    int a = 36, b = 0;  // measured on the 64^2 base UNet (profiles/README.md round 2): 36 k-blocks per split at 8x8, no split at 16x16
+    // measured on the 64^2 / 256^2 stage UNets (profiles/README.md round 2, item 4): 18 k-blocks per split for <= 16x16 images is the
+    // fastest at B = 1-4 (the wavefront's chain-bound batches: 4.97 -> 4.68 ms, 4.11 -> 3.69 ms) and costs 10 % at B = 16
+    int a = 18, b = 18;
     if (const char* e = getenv("KD_SPLITK_TARGETS")) sscanf(e, "%d,%d", &a, &b);
     tgt_small = a;
     tgt_mid = b;
