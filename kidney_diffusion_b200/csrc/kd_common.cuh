@@ -140,8 +140,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 __device__ __forceinline__ void apply_act8(float* v, int act) {
   if (act == KD_ACT_NONE) return;
   if (act == KD_ACT_SILU) {
+    // every caller rounds the result to fp16 right after: the one-MUFU tanh form (abs error <= |x| * 2.4e-4, half an fp16 ulp)
+    // instead of ex2 + rcp.  The pixel-shuffle upsample convs are bound by their epilogue's issue rate (ncu r02_shuffle: XU pipe
+    // 37 %, 2 epilogue warps per scheduler), and the GroupNorm fallback pass now rounds exactly like the conv's fused prologue.
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    for (int j = 0; j < 8; ++j) v[j] = silu_from_half_arg(0.5f * v[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act);

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 ncu --query-metrics 2>/dev/null | grep -i -E "tensor|pipe_tc|tmem|utc" > gpurun_out/r02_ncu_tensor_metrics.txt
-declare -A KERN=( [pre128]=conv_gemm_halo [pre256]=conv_gemm_halo [res1x1]=conv_gemm_pair [c1x1]=conv_gemm_pair [init]=init_conv [final]=final_conv [gca_pool]=gca_pool_kernel [attn]=attn_mqa_tc [cublas]="gemm|cutlass|nvjet|sm100" )
+declare -A KERN=( [pre128]=conv_gemm_halo [pre256]=conv_gemm_halo [res1x1]=conv_gemm_pair [c1x1]=conv_gemm_pair [shuffle]=conv_gemm_pair [init]=init_conv [final]=final_conv [gca_pool]=gca_pool_kernel [attn]=attn_mqa_tc [cublas]="gemm|cutlass|nvjet|sm100" )
 for t in "$@"; do
   python profiles/ncu_targets.py $t > gpurun_out/r02_${t}_plain.log 2>&1 || { echo "$t: plain run failed"; tail -3 gpurun_out/r02_${t}_plain.log; continue; }
   cat gpurun_out/r02_${t}_plain.log

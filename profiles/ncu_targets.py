@@ -1,6 +1,6 @@
 """One shipped kernel variant per invocation, launched a few times on the shape it has inside the B = 8 1024^2 patch-step, for
 `ncu --set full -k regex:<kernel> -s 2 -c 1` (profiles/README.md).  Also prints the CUDA-event time and algorithmic TFLOP/s / GB/s.
-Targets: pre128 pre256 res1x1 c1x1 init final gca_pool attn cublas
+Targets: pre128 pre256 res1x1 c1x1 shuffle init final gca_pool attn cublas
 Usage: python profiles/ncu_targets.py <target> [B]"""
 import os
 import sys
@@ -84,6 +84,11 @@ elif target == "attn":      # attn_mqa_tc_kernel (tcgen05; set KD_ATTN_LEGACY=1 
     qkv = act(B, N, 512 + 128)
     kv = ops.kv_assemble(qkv, 512, None, torch.randn(2, 64, device=dev))
     run(lambda: ops.attn_mqa(qkv, kv, 8, 0.125), 4.0 * B * 8 * N * (N + 1) * 64, B * N * 2 * (640 + 512))
+elif target == "shuffle":   # conv_gemm_pair_kernel<256, 5, 0>: PixelShuffleUpsample 1x1 128 -> 512 + SiLU at 512^2, stored as 1024^2 x 128
+    S = 512
+    xa, w, bias = act(B, S, S, 128), act(512, 128), torch.randn(512, device=dev)
+    px = B * S * S
+    run(lambda: ops.conv_gemm(xa, w, bias, ksize=1, act=ops.ACT_SILU, out_mode=1), 2.0 * px * 128 * 512, px * 2 * (128 + 512))
 elif target == "cublas":    # calibration of the tensor-pipe counter: the library GEMM MEASURED_PEAKS.json's peak comes from
     a, b = torch.randn(8192, 8192, device=dev).bfloat16(), torch.randn(8192, 8192, device=dev).bfloat16()
     run(lambda: a @ b, 2.0 * 8192 ** 3, 3 * 8192 * 8192 * 2)
