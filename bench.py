@@ -559,7 +559,7 @@ def run_b200(args):
                                 l2="inputs larger than L2 (activations >= 0.27 GB per tensor per patch)", state_dtype="f32",
                                 plan=dict(batches=len(plan.batches), batch_sizes=plan.batch_sizes().get(3), policy=str(plan.policy),
                                           simulated_busy_fraction=plan.busy_fraction()),
-                                transport=info.get("transport"), border_bytes_exchanged=float(sent.item()),
+                                transport=info.get("transport"), border_bytes_exchanged=float(sent.item()), trace_rank0=info.get("trace"),
                                 unet_gflop_per_patch_step=UNET3_GFLOP_PER_SAMPLE_1024),
                     roofline=dict(bound="tensor", achieved=value * UNET3_GFLOP_PER_SAMPLE_1024 / 1e3 / world, peak=peaks["tf_sustained"], unit="TFLOP/s",
                                   frac=value * UNET3_GFLOP_PER_SAMPLE_1024 / 1e3 / world / peaks["tf_sustained"], traffic=None,

@@ -537,11 +537,16 @@ def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, 
             if prev_owner[k] == rank and dst != rank:
                 transport.post(dst, (prev_stage, k, "lowres"), lowres_image[k].to(device).reshape(3, Sp, Sp))
 
+    trace = [] if (os.environ.get("KD_GRID_TRACE") and device.type == "cuda") else None  # per-batch CUDA events: inputs / sample / post
     for batch in plan.for_rank(rank):
         u, mine = batch.stage, batch.patches
         S = PATCH_SIZES[u]
         ov = int(overlap * S)
         inpaints, masks = [], []
+        if trace is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            t_host0 = time.time()
         for k in mine:
             i, j = patch_pos[k]
             strips = {}
@@ -568,12 +573,18 @@ def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, 
                             for k in mine], 0)
         elif lowres_image is not None:
             Sp = PATCH_SIZES[prev_stage]
-            lr = torch.cat([lowres_image[k].to(device) if (prev_owner is None or prev_owner[k] == rank)
+            lr = torch.cat([lowres_image[k].to(device, non_blocking=True) if (prev_owner is None or prev_owner[k] == rank)
                             else transport.fetch(prev_owner[k], (prev_stage, k, "lowres"), (3, Sp, Sp), device).reshape(1, 3, Sp, Sp)
                             for k in mine], 0)
         ci = None if cond_image is None else torch.stack([cond_image[k] for k in mine]).to(device)
+        if trace is not None:
+            ev[1].record()
+            t_host1 = time.time()
         out = imagens[u].sample(batch_size=len(mine), cond_images=ci, start_image_or_video=lr, inpaint_images=torch.stack(inpaints),
                                 inpaint_masks=torch.stack(masks), noise_key=[_noise_key(mag_level, k) for k in mine], **sample_kw(u))
+        if trace is not None:
+            ev[2].record()
+            t_host2 = time.time()
         for b, k in enumerate(mine):
             results[u][k] = out[b:b + 1].contiguous()
         if transport is not None:  # push what dependents on other ranks need, as soon as it exists
@@ -583,6 +594,9 @@ def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, 
                         transport.post(owner[(u, index[q])], (u, k, kind), _strip_of(results[u][k], kind, S, ov, orientation)[0])
                 if (u + 1) in plan.stages and owner[(u + 1, k)] != rank:
                     transport.post(owner[(u + 1, k)], (u, k, "lowres"), results[u][k].reshape(3, S, S))
+        if trace is not None:
+            ev[3].record()
+            trace.append((u, len(mine), ev, (t_host1 - t_host0, t_host2 - t_host1, time.time() - t_host2)))
     if transport is not None:
         transport.finish()
     last = stages[-1]
@@ -592,6 +606,18 @@ def _run(mag_level, stages, args, lowres_image, cond_image, patch_pos, overlap, 
                     batch_sizes={str(u): v for u, v in plan.batch_sizes().items()}, plan_busy_fraction=plan.busy_fraction(),
                     transport="none (single rank)" if transport is None else transport.name,
                     bytes_sent_this_rank=0 if transport is None else transport.bytes_sent, host_wall_s=time.time() - t_wall)
+    if trace is not None:  # device time of the three phases (waiting for neighbours' strips counts as "inputs") and host time spent issuing them
+        torch.cuda.synchronize(device)
+        tot = dict(batches=len(trace), inputs_ms=0.0, sample_ms=0.0, post_ms=0.0, host_inputs_ms=0.0, host_sample_ms=0.0, host_post_ms=0.0)
+        for _, _, ev, host in trace:
+            tot["inputs_ms"] += ev[0].elapsed_time(ev[1])
+            tot["sample_ms"] += ev[1].elapsed_time(ev[2])
+            tot["post_ms"] += ev[2].elapsed_time(ev[3])
+            tot["host_inputs_ms"] += host[0] * 1e3
+            tot["host_sample_ms"] += host[1] * 1e3
+            tot["host_post_ms"] += host[2] * 1e3
+        tot["span_ms"] = trace[0][2][0].elapsed_time(trace[-1][2][3]) if trace else 0.0
+        LAST_RUN["trace"] = tot
     out.plan = plan
     if transport is not None:
         if hasattr(transport, "recycle"):

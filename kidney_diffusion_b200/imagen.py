@@ -138,7 +138,10 @@ class StageRun:
         self.times = schedule.sampling_times(spec.num_timesteps)
         self.num_steps = len(self.times)
         self.scal = [schedule.step_scalars(self.sched, t, tn) for t, tn in self.times]
-        self.time_table = torch.tensor([[s["log_snr"]] * B for s in self.scal], device=device, dtype=torch.float32)
+        # pinned + non_blocking: a pageable host-to-device copy would make the host wait for everything queued on the stream, i.e.
+        # for the previous batch of a patch-grid run, and the GPU would idle while the host prepares this one
+        tt = torch.tensor([[s["log_snr"]] * B for s in self.scal], dtype=torch.float32)
+        self.time_table = tt.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else tt.to(device)
         self.ws = torch.empty(ops.lib().kd_dynthresh_workspace_bytes(B), device=device, dtype=torch.uint8)
 
     def step(self, step, r=0):
