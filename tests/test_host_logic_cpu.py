@@ -79,3 +79,44 @@ def test_argument_validation_reports_through_kd_last_error(lib):
     assert rc != 0
     assert b"multiples of 64" in lib.kd_last_error()
     assert lib.kd_set_conv_impl(3) != 0 and lib.kd_set_conv_impl(7) != 0 and lib.kd_set_conv_impl(0) == 0
+
+
+def test_precise_namespace_covers_every_op_the_executor_uses():
+    """UnetExecutor runs the same forward code over `ops` (fp16 tensor-core path) or `ops_f32` (precise path): every op it
+    reaches through `self.K` must exist in both namespaces, except the tensor-core-only fast paths it guards with `self.precise`."""
+    import inspect
+    import re
+
+    from kidney_diffusion_b200 import ops, ops_f32, unet_exec
+
+    src = inspect.getsource(unet_exec.UnetExecutor)
+    used = set(re.findall(r"self\.K\.([A-Za-z_0-9]+)", src))
+    fast_only = {"init_conv", "init_conv_kp", "im2col_nchw", "gemm_rows", "gn_finalize_oct", "gn_apply"}   # behind `if self.precise: ... return`
+    precise_only = {"groupnorm", "init_conv_nchw"}
+    assert fast_only <= used and precise_only <= used
+    for name in sorted(used - precise_only):
+        assert hasattr(ops, name), f"ops.{name} missing"
+    for name in sorted(used - fast_only):
+        assert hasattr(ops_f32, name), f"ops_f32.{name} missing"
+    assert ops_f32.ACT_DTYPE.is_floating_point and ops_f32.ACT_DTYPE.itemsize == 4 and ops.ACT_DTYPE.itemsize == 2
+    assert not ops_f32.conv_pre_supported(1, 64, 64, 128, 0, 128)
+    with pytest.raises(NotImplementedError):
+        ops_f32.linear_attention()
+
+
+def test_precision_switch_on_the_host_side():
+    import torch
+
+    from kidney_diffusion_b200 import Imagen, Unet
+
+    u = Unet(dim=64, dim_mults=(1, 2), num_resnet_blocks=1, layer_attns=False, layer_cross_attns=False, cond_on_text=False, text_embed_dim=None)
+    assert Unet.precision == "fp16" and u.precision == "fp16"
+    im = Imagen(unets=(u,), image_sizes=(32,), timesteps=(2,), condition_on_text=False)
+    u = im.unets[0]
+    im._graphs["stale"] = object()
+    assert im.set_precision("fp32") is im
+    assert u.precision == "fp32" and im._graphs == {} and Unet.precision == "fp16"   # per instance, captured graphs dropped
+    with pytest.raises(AssertionError):
+        im.set_precision("bf16")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):   # either precision needs the GPU: nothing falls back to torch
+        u(torch.zeros(1, 3, 32, 32), torch.zeros(1))
