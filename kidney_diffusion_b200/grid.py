@@ -385,7 +385,11 @@ def load_model(mag_level, unet_number, device, args, provider=None):
     key = (mag_level, unet_number, str(device), id(provider))
     if key not in _MODEL_CACHE:
         _MODEL_CACHE[key] = provider(mag_level, unet_number, device, args)
-    return _MODEL_CACHE[key]
+    model = _MODEL_CACHE[key]
+    precision = getattr(args, "precision", None)  # "fp32": the precise CUDA-core path of every UNet (validation runs)
+    if precision is not None and hasattr(model, "set_precision"):
+        model.set_precision(precision)
+    return model
 
 
 def _device_for(args, rank):

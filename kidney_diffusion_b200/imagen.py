@@ -241,10 +241,13 @@ class Imagen(nn.Module):
         """"fp16" (default): tcgen05 tensor-core path.  "fp32": the precise CUDA-core path of every stage's UNet (csrc/kd_precise.cu;
         per-step parity 1e-4 against the fp32 reference, 20-50x slower).  The sampler update is fp32 in both."""
         assert precision in ("fp16", "fp32"), precision
+        changed = False
         for u in self.unets:
-            if hasattr(u, "precision"):
+            if hasattr(u, "precision") and u.precision != precision:
                 u.precision = precision
-        self._graphs = {}
+                changed = True
+        if changed:  # captured step graphs belong to the other executor
+            self._graphs = {}
         return self
 
     def normalize_img(self, img):

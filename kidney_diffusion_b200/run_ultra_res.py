@@ -6,7 +6,8 @@
 One process per GPU (the reference spawns `--num_gpus` worker processes itself; here the launcher does, and `--num_gpus` is
 accepted and ignored).  The flow is the reference's main(): magnification 0 image -> 6 400^2 magnification-1 image -> magnification-2
 image, each saved as JPEG by rank 0.  Extra flags: --seed (reproducible noise), --stage_major (the reference's stage order instead
-of the pipelined plan), --max_mag (stop after this magnification level).
+of the pipelined plan), --max_mag (stop after this magnification level), --precision fp32 (every UNet on the fp32 CUDA-core path:
+validation runs, 20-50x slower).
 """
 from __future__ import annotations
 
@@ -31,6 +32,7 @@ def parse_args(argv=None):
     parser.add_argument("--seed", type=int, default=None)
     parser.add_argument("--stage_major", action="store_true")
     parser.add_argument("--max_mag", type=int, default=2)
+    parser.add_argument("--precision", choices=("fp16", "fp32"), default=None)
     return parser.parse_args(argv)
 
 
