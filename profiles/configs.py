@@ -57,6 +57,12 @@ def cfg1(no_cpu):
         cpu_s = time.perf_counter() - t0
         line.update(cpu_seconds=cpu_s, cpu_cores=os.cpu_count(), cpu_kind="port (fp32 PyTorch oracle)", speedup=cpu_s / warm,
                     final_sample_rel_l2_vs_oracle=rel_l2(out, ref), tolerance=1e-2)
+        pi.set_precision("fp32")  # the precise CUDA-core path on the same model and noise
+        timed(lambda: pi.sample(batch_size=4, use_tqdm=False, device=dev))
+        out32, s32 = timed(lambda: pi.sample(batch_size=4, use_tqdm=False, device=dev))
+        line.update(fp32_path_seconds=s32, fp32_path_final_sample_rel_l2_vs_oracle=rel_l2(out32, ref), fp32_tolerance=1e-4,
+                    fp16_path_vs_fp32_path_rel_l2=rel_l2(out, out32))
+        pi.set_precision("fp16")
     print(json.dumps(line), flush=True)
 
 
