@@ -361,6 +361,12 @@ int kd_gate_residual_f32(const float* h, const float* gate /* [B, C] */, const f
  * out [B, N, heads * 64].  Replaces Attention.forward / CrossAttention.forward after their projections. */
 int kd_attn_f32(const float* q, long ldq, const float* k, long ldk, long k_batch, int k_head, const float* v, long ldv, long v_batch, int v_head,
                 float* out, int B, int N, int J, int heads, float scale, kd_stream_t stream);
+/* LinearAttention / LinearCrossAttention in fp32: depthwise 3x3 (zero padding, no bias; w [C,3,3]); then for every (sample, head)
+ * ctx = softmax over the J key positions of k (per head-dim column) transposed times v, and out = act(scale * softmax_d(q) ctx).
+ * q [B, N, ldq] (head h at column 64 h); k / v rows of length ldkv with head h at column 64 h, J positions, sample stride kv_batch. */
+int kd_dwconv3x3_f32(const float* x /* NHWC */, const float* w, float* y, int B, int H, int W, int C, kd_stream_t stream);
+int kd_linattn_f32(const float* q, long ldq, const float* k, const float* v, long ldkv, long kv_batch, int B, int N, int J, int heads, float scale,
+                   int act, float* ctx /* [B, heads, 64, 64] workspace / result */, float* out /* [B, N, heads*64] */, kd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,8 @@ SIGNATURES = {
     "kd_softmax_pool_f32": (c_int, [_P, _P, _I, _L, _I, _P, _P, _P, _P]),
     "kd_gate_residual_f32": (c_int, [_P, _P, _P, _P, _I, _L, _I, _P]),
     "kd_attn_f32": (c_int, [_P, _L, _P, _L, _L, _I, _P, _L, _L, _I, _P, _I, _I, _I, _I, _F, _P]),
+    "kd_dwconv3x3_f32": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "kd_linattn_f32": (c_int, [_P, _L, _P, _P, _L, _L, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "kd_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "kd_peer_free": (c_int, [_P]),
     "kd_peer_export": (c_int, [_P, _P]),

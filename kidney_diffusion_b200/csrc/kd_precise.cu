@@ -11,6 +11,8 @@
 //   kd_rowdot_f32, kd_softmax_stats_f32, kd_softmax_pool_f32, kd_pool_finalize_f32, kd_gate_residual_f32   (GlobalContext)
 //   kd_attn_f32           softmax attention, head dim 64, explicit key / value strides  (Attention: one shared K/V head;
 //                         CrossAttention: per-head K/V)
+//   kd_dwconv3x3_f32, kd_linattn_f32   LinearAttention / LinearCrossAttention (depthwise 3x3 of q | k | v; softmax_n(k)^T v context;
+//                         softmax_d(q) context)
 #include "kd_common.cuh"
 
 namespace {
@@ -322,6 +324,101 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__
   *reinterpret_cast<float2*>(out + (bn * heads + h) * 64 + 2 * lane) = make_float2(a0 * inv, a1 * inv);
 }
 
+// ---------------------------------------------------------------------------------------------- linear attention (head dim 64)
+__global__ void __launch_bounds__(256) dwconv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                                            int H, int W, int C, long total) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    long pix = i / C;
+    const int xw = (int)(pix % W);
+    pix /= W;
+    const int yh = (int)(pix % H);
+    const long b = pix / H;
+    float acc = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yh + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = xw + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        acc = fmaf(x[((b * H + iy) * W + ix) * C + c], w[c * 9 + ky * 3 + kx], acc);
+      }
+    }
+    y[i] = acc;
+  }
+}
+
+// ctx[b][h][d][e] = sum_n softmax_n(k[., d])[n] * v[n][e]: one block per (sample, head); thread -> (d = tid / 4, 16 values of e);
+// positions in order, fp32
+__global__ void __launch_bounds__(256) linattn_ctx_f32_kernel(const float* __restrict__ k, const float* __restrict__ v, long ld, long batch_stride,
+                                                              int N, int heads, float* __restrict__ ctx) {
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const float* kp = k + (long)b * batch_stride + h * 64;
+  const float* vp = v + (long)b * batch_stride + h * 64;
+  __shared__ float s_max[4][64];
+  {
+    const int d = threadIdx.x & 63, part = threadIdx.x >> 6;
+    float m = -INFINITY;
+    for (int n = part; n < N; n += 4) m = fmaxf(m, kp[(long)n * ld + d]);
+    s_max[part][d] = m;
+  }
+  __syncthreads();
+  const int d = threadIdx.x >> 2, e0 = (threadIdx.x & 3) * 16;
+  const float m = fmaxf(fmaxf(s_max[0][d], s_max[1][d]), fmaxf(s_max[2][d], s_max[3][d]));
+  float acc[16], l = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+  for (int n = 0; n < N; ++n) {
+    const float wgt = expf(kp[(long)n * ld + d] - m);
+    const float4* v4 = reinterpret_cast<const float4*>(vp + (long)n * ld + e0);
+    l += wgt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = v4[q];
+      acc[q * 4 + 0] = fmaf(wgt, t.x, acc[q * 4 + 0]);
+      acc[q * 4 + 1] = fmaf(wgt, t.y, acc[q * 4 + 1]);
+      acc[q * 4 + 2] = fmaf(wgt, t.z, acc[q * 4 + 2]);
+      acc[q * 4 + 3] = fmaf(wgt, t.w, acc[q * 4 + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+  float* o = ctx + (((long)b * heads + h) * 64 + d) * 64 + e0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = acc[j] * inv;
+}
+
+// out[b][n][h*64 + e] = act(scale * sum_d softmax_d(q[b][n][h*64 + .])[d] * ctx[b][h][d][e]): one warp per (sample, position, head)
+__global__ void __launch_bounds__(256) linattn_apply_f32_kernel(const float* __restrict__ q, long ldq, const float* __restrict__ ctx,
+                                                                float* __restrict__ out, int B, int N, int heads, float scale, int act) {
+  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long)B * N * heads) return;
+  const int h = (int)(wid % heads);
+  const long bn = wid / heads;
+  const int b = (int)(bn / N);
+  const float2 qv = *reinterpret_cast<const float2*>(q + bn * ldq + h * 64 + 2 * lane);
+  float m = fmaxf(qv.x, qv.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float p0 = expf(qv.x - m), p1 = expf(qv.y - m);
+  float l = p0 + p1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  const float* cp = ctx + ((long)b * heads + h) * 4096 + 2 * lane;
+  float a0 = 0.0f, a1 = 0.0f;
+  for (int d = 0; d < 64; ++d) {
+    const float pd = __shfl_sync(0xffffffffu, (d & 1) ? p1 : p0, d >> 1);
+    const float2 c = *reinterpret_cast<const float2*>(cp + d * 64);
+    a0 = fmaf(pd, c.x, a0);
+    a1 = fmaf(pd, c.y, a1);
+  }
+  const float f = scale / l;
+  *reinterpret_cast<float2*>(out + (bn * heads + h) * 64 + 2 * lane) = make_float2(act_precise(a0 * f, act), act_precise(a1 * f, act));
+}
+
 inline unsigned grid_1d(long total, int block, int cap_per_sm = 16) {
   long blocks = (total + block - 1) / block;
   const long cap = (long)kd_num_sms() * cap_per_sm;
@@ -433,6 +530,31 @@ extern "C" int kd_attn_f32(const float* q, long ldq, const float* k, long ldk, l
              "kd_attn_f32: 8-byte alignment of q / k / v rows required");
   const long warps = (long)B * N * heads;
   attn_f32_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(q, ldq, k, ldk, k_batch, k_head, v, ldv, v_batch, v_head, out, B, N, J, heads, scale);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_dwconv3x3_f32(const float* x, const float* w, float* y, int B, int H, int W, int C, kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && C > 0, "kd_dwconv3x3_f32: bad argument");
+  const long total = (long)B * H * W * C;
+  dwconv3x3_f32_kernel<<<grid_1d(total, 256), 256, 0, stream>>>(x, w, y, H, W, C, total);
+  KD_LAUNCH_CHECK();
+  return KD_OK;
+}
+
+extern "C" int kd_linattn_f32(const float* q, long ldq, const float* k, const float* v, long ldkv, long kv_batch, int B, int N, int J, int heads,
+                              float scale, int act, float* ctx /* [B, heads, 64, 64] */, float* out /* [B, N, heads * 64] */,
+                              kd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KD_REQUIRE(q && k && v && ctx && out && B > 0 && N > 0 && J > 0 && heads > 0, "kd_linattn_f32: bad argument");
+  KD_REQUIRE(ldq % 2 == 0 && ldkv % 4 == 0 && kv_batch % 4 == 0 && (reinterpret_cast<uintptr_t>(q) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 3) == 0,
+             "kd_linattn_f32: alignment of q (8 bytes) / v rows (16 bytes) required");
+  linattn_ctx_f32_kernel<<<B * heads, 256, 0, stream>>>(k, v, ldkv, kv_batch, J, heads, ctx);
+  KD_LAUNCH_CHECK();
+  const long warps = (long)B * N * heads;
+  linattn_apply_f32_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(q, ldq, ctx, out, B, N, heads, scale, act);
   KD_LAUNCH_CHECK();
   return KD_OK;
 }

@@ -189,8 +189,40 @@ def init_conv_nchw(img, ksize, w, bias, addend, out):
     return conv_gemm(img.permute(0, 2, 3, 1).contiguous(), w, bias, ksize=ksize, addend=addend, out=out)
 
 
-def dwconv3x3(*args, **kwargs):
-    raise NotImplementedError("linear attention has no fp32 path: use precision='fp16' with use_linear_attn / use_linear_cross_attn")
+@_timed
+def dwconv3x3(x, w):
+    """Depthwise 3x3 convolution (zero padding, no bias): x NHWC fp32 [B,H,W,C], w fp32 [C,3,3]."""
+    _chk(x, "x")
+    _chk(w, "w")
+    B, H, W, C = x.shape
+    assert w.shape == (C, 3, 3)
+    y = torch.empty_like(x)
+    check(lib().kd_dwconv3x3_f32(_ptr(x), _ptr(w), _ptr(y), B, H, W, C, _stream()), "kd_dwconv3x3_f32")
+    _count()
+    return y
 
 
-linear_attention = dwconv3x3
+@_timed
+def linear_attention(qkv, heads, scale, ctx_kv=None, act=ACT_SILU, pixels_kv=True):
+    """Same contract as ops.linear_attention on fp32 tensors: qkv [B, N, 3*heads*64] (q | k | v), or only q with pixels_kv=False;
+    ctx_kv fp32 [B, J, 2*heads*64] (k | v of the context tokens) -> [B, N, heads*64]."""
+    _chk(qkv, "qkv")
+    B, N, ld = qkv.shape
+    inner = heads * 64
+    assert ld == (3 * inner if pixels_kv else inner)
+    parts = []
+    if pixels_kv:
+        parts.append(qkv[:, :, inner:])
+    if ctx_kv is not None:
+        assert ctx_kv.shape[0] == B and ctx_kv.shape[2] == 2 * inner
+        parts.append(ctx_kv)
+    assert parts, "linear attention needs keys: pixels, context tokens or both"
+    kv = parts[0] if len(parts) == 1 and parts[0].is_contiguous() else torch.cat(parts, 1).contiguous()  # [B, J, 2*inner]: k | v, layout glue
+    J = kv.shape[1]
+    ctx = torch.empty((B, heads, 64, 64), device=qkv.device, dtype=F32)
+    out = torch.empty((B, N, inner), device=qkv.device, dtype=F32)
+    k, v = kv[:, :, :inner], kv[:, :, inner:]
+    check(lib().kd_linattn_f32(_ptr(qkv), ld, _ptr(k), _ptr(v), kv.stride(1), kv.stride(0), B, N, J, heads, float(scale), act, _ptr(ctx), _ptr(out),
+                               _stream()), "kd_linattn_f32")
+    _count(2)
+    return out

@@ -234,9 +234,17 @@ def test_conditioned_cascade_fp32(cuda_lib):
     assert err < TOL32
 
 
-def test_linear_attention_has_no_fp32_path(cuda_lib):
-    kw = dict(U1_KW, layer_attns=(False, False, True, True), use_linear_attn=(False, True, False, False))
-    _, pu = make_pair(kw, lowres_cond=False, seed=3)
+def test_linear_attention_fp32(cuda_lib):
+    """LinearAttentionTransformerBlock and LinearCrossAttention on the fp32 path (use_linear_attn / use_linear_cross_attn)."""
+    kw = dict(U1_KW, layer_attns=(False, False, True, True), use_linear_attn=(False, True, False, False),
+              use_linear_cross_attn=(False, True, False, False))
+    ou, pu = make_pair(kw, lowres_cond=False, seed=77)
+    g = torch.Generator().manual_seed(5)
+    x, t = torch.randn(2, 3, 32, 32, generator=g), torch.tensor([2.18, -0.5])
+    with torch.no_grad():
+        ref = ou(x, t)
     pu.precision = "fp32"
-    with pytest.raises(NotImplementedError):
-        pu(torch.randn(1, 3, 32, 32, device="cuda"), torch.tensor([1.0], device="cuda"))
+    out = pu(x.cuda(), t.cuda())
+    err = rel_l2(out, ref)
+    print(f"[u1 with linear attention] fp32 path vs oracle {err:.3e}")
+    assert err < TOL32
