@@ -57,8 +57,24 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml_rows, self.nvml = [], None
+        try:  # NVML (what nvidia-smi itself reads) answers in microseconds: a dense second series for short timed regions, where
+            import pynvml  # one nvidia-smi process (0.3-0.8 s each on these boxes) may yield only one or two samples
+
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        nv, h = self.nvml
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(reasons_fn(h))
+        self.nvml_rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), mask))
 
     def run(self):
+        if self.nvml is not None:
+            threading.Thread(target=self._nvml_loop, daemon=True).start()
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -69,15 +85,32 @@ class ClockSampler(threading.Thread):
                 pass
             self.stop_flag.wait(0.2)
 
+    def _nvml_loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._nvml_sample()
+            except Exception:
+                return
+            self.stop_flag.wait(0.02)
+
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows))
+        reasons = {n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}
+        out = dict(samples=len(self.rows), source="nvidia-smi")
+        if self.nvml_rows:  # NVML reason bits: sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal_slowdown 0x20, hw_thermal_slowdown 0x40
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            nv_sm = [r[0] for r in self.nvml_rows]
+            reasons |= {n for r in self.nvml_rows for n, b in bits.items() if r[2] & b}
+            out.update(nvml_samples=len(nv_sm), nvml_sm_mhz=statistics.median(nv_sm), nvml_sm_min_mhz=min(nv_sm))
+            if len(sm) < 3:  # too few nvidia-smi samples inside a short region: report the dense series
+                sm, mx = nv_sm, [r[1] for r in self.nvml_rows]
+                out["source"] = "nvml (fewer than 3 nvidia-smi samples fell inside the timed region)"
+        out.update(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons))
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
