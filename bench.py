@@ -70,7 +70,11 @@ class ClockSampler(threading.Thread):
         nv, h = self.nvml
         reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         mask = int(reasons_fn(h))
-        self.nvml_rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), mask))
+        try:
+            watts = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+        except Exception:
+            watts = None
+        self.nvml_rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), mask, watts))
 
     def run(self):
         if self.nvml is not None:
@@ -106,6 +110,9 @@ class ClockSampler(threading.Thread):
             nv_sm = [r[0] for r in self.nvml_rows]
             reasons |= {n for r in self.nvml_rows for n, b in bits.items() if r[2] & b}
             out.update(nvml_samples=len(nv_sm), nvml_sm_mhz=statistics.median(nv_sm), nvml_sm_min_mhz=min(nv_sm))
+            watts = [r[3] for r in self.nvml_rows if len(r) > 3 and r[3] is not None]
+            if watts:
+                out["power_w"] = statistics.median(watts)
             if len(sm) < 3:  # too few nvidia-smi samples inside a short region: report the dense series
                 sm, mx = nv_sm, [r[1] for r in self.nvml_rows]
                 out["source"] = "nvml (fewer than 3 nvidia-smi samples fell inside the timed region)"
